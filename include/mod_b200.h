@@ -1,0 +1,190 @@
+/*
+ * mod_b200.h -- C ABI of the B200-native scene-flow / motion-segmentation hot path.
+ *
+ * The reference (ActiveIntelligentSystemsLab/moving_object_detector) has no FFI: its seams are C++ method
+ * boundaries inside two ROS processes.  This header introduces a thin C ABI exactly at those two seams so the
+ * unchanged ROS host side (node / nodelet, dynamic_reconfigure, topics, messages) can call the CUDA path:
+ *
+ *   seam 1  SceneFlowConstructor::construct()                scene_flow_constructor/src/scene_flow_constructor.cpp:91-147
+ *           (DisparityImageProcessor::toPointCloud x2         disparity_image_proc/src/disparity_image_processor.cpp:86-103,
+ *            transformPCPreviousToNow :409-429, calculateStaticOpticalFlow :65-89, constructVelocityPC :149-212)
+ *   seam 2  ClustererNodelet::clustering() + publishMovingObjects()
+ *                                                             scene_flow_clusterer/src/clusterer_nodelet.cpp:85-95,324-343
+ *
+ * All entry points are extern "C", take plain pointers and sizes, never throw, and return a mod_status.
+ * Parameters that dynamic_reconfigure can change (cfg/SceneFlowConstructor.cfg:8-9, cfg/Clusterer.cfg:8-11) are
+ * passed BY VALUE PER CALL, never latched in the context.
+ *
+ * Threading: one call at a time per context (the reference joins the previous construct() worker before starting
+ * the next, scene_flow_constructor.cpp:389-392, and the clusterer callback queue is single-threaded,
+ * clusterer_nodelet.cpp:25,35).  Contexts are independent (one per GPU / per stream).
+ *
+ * There is NO CPU fallback: every compute entry point returns MOD_ERR_CUDA / MOD_ERR_NO_DEVICE when no sm_100a
+ * device is usable.
+ */
+#ifndef MOD_B200_H_
+#define MOD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOD_B200_ABI_VERSION 1
+
+typedef struct mod_ctx mod_ctx;
+
+typedef enum {
+  MOD_OK = 0,
+  MOD_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, size larger than the context was created for   */
+  MOD_ERR_CAPACITY = -2,      /* more moving objects than max_objs; *n_objs holds the true count, objs is filled   */
+                              /* up to max_objs (the reference's message array is unbounded)                       */
+  MOD_ERR_INVALID_PARAM = -3, /* parameter value at which the reference itself throws / is undefined               */
+                              /* (cluster_size == 0: cluster.at(0) on an empty cluster, clusterer_nodelet.cpp:174; */
+                              /*  neighbor_distance < 0)                                                           */
+  MOD_ERR_CUDA = -4,          /* a CUDA runtime call failed; see mod_last_error()                                  */
+  MOD_ERR_NO_DEVICE = -5,     /* no CUDA device / not compute capability 10.x                                      */
+  MOD_ERR_CLUSTER_SLOTS = -6  /* more surviving clusters in one frame than the context's max_clusters              */
+} mod_status;
+
+/* left CameraInfo: P[0], P[5], P[2], P[6], P[3], P[7] -- what image_geometry::PinholeCameraModel::fx() fy() cx()
+ * cy() Tx() Ty() return after fromCameraInfo (disparity_image_processor.cpp:7,14; scene_flow_constructor.cpp:370-371) */
+typedef struct { double fx, fy, cx, cy, Tx, Ty; } mod_camera;
+
+/* stereo_msgs/DisparityImage as consumed at disparity_image_processor.cpp:3-15: float32 scalars, 32FC1 image with a
+ * byte row stride (image.step).  `data` is a HOST pointer in the host entry points. */
+typedef struct {
+  float f, T, min_disparity, max_disparity;
+  const float* data;
+  int32_t step_bytes;
+} mod_disparity;
+
+/* geometry_msgs/Transform exactly as produced at scene_flow_constructor.cpp:248-249 (translation + quaternion) */
+typedef struct { double tx, ty, tz, qx, qy, qz, qw; } mod_transform;
+
+/* dynamic_reconfigure SceneFlowConstructor (cfg/SceneFlowConstructor.cfg:8-9); max_color_velocity is carried for
+ * interface completeness -- no computation in the reference reads it (scene_flow_constructor.cpp:406). */
+typedef struct { int32_t dynamic_flow_diff; double max_color_velocity; } mod_sf_params;
+
+/* dynamic_reconfigure Clusterer (cfg/Clusterer.cfg:8-11; members at clusterer_nodelet.h:54-57) */
+typedef struct {
+  int32_t cluster_size;
+  double depth_diff;
+  double dynamic_speed;
+  int32_t neighbor_distance;
+} mod_cl_params;
+
+/* moving_object_msgs/MovingObject (msg/MovingObject.msg:3-7).  The reference computes centre, velocity and
+ * bounding box in float and widens to the message's float64 fields (clusterer_nodelet.cpp:151-181), so float is
+ * lossless here; orientation is always (0,0,0,1) (clusterer_nodelet.cpp:163-166). */
+typedef struct {
+  int32_t id;
+  float center[3];
+  float velocity[3];
+  float bbox[3];
+  int32_t n_points;
+} mod_object;
+
+/* One frame pair of the device-resident batched path.  All pointers are DEVICE pointers to dense images
+ * (row stride = w elements): disparity 32FC1, flow 32FC2.  In a sequence disp_prev of pair i is simply
+ * disp_now of pair i-1 (scene_flow_constructor.cpp:398). */
+typedef struct {
+  const float* disp_now;
+  const float* disp_prev;
+  const float* flow_xy;
+  float f_now, T_now, min_disparity_now, max_disparity_now;
+  float f_prev, T_prev, min_disparity_prev, max_disparity_prev;
+  mod_transform prev2now;
+  double dt_sec; /* (stamp_now - stamp_prev).toSec(), scene_flow_constructor.cpp:162-164 */
+} mod_pair_dev;
+
+/* Per-frame counters of the last call (diagnostics; the reference only logs wall time). */
+typedef struct {
+  int32_t n_dynamic;   /* pixels in dynamic_map_ (clusterer_nodelet.cpp:40-54)                 */
+  int32_t n_clusters;  /* clusters that survived removeSmallClusters (clusterer_nodelet.cpp:354-393) */
+  int32_t n_objects;   /* accepted MovingObjects                                                */
+  int32_t status;      /* MOD_OK, MOD_ERR_CAPACITY or MOD_ERR_CLUSTER_SLOTS for this frame      */
+} mod_frame_stats;
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` able to process frames up to max_w x max_h, max_batch frame pairs per
+ * batched call and max_clusters surviving clusters per frame (0 = default 4096).  Owns device workspaces, one
+ * stream and pinned staging.  Returns MOD_ERR_NO_DEVICE when there is no usable sm_100a GPU. */
+int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx);
+void mod_destroy(mod_ctx* ctx);
+/* Message of the last error on this context ("" if none); valid until the next call on the context. */
+const char* mod_last_error(const mod_ctx* ctx);
+int mod_abi_version(void);
+
+/* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
+void* mod_host_alloc(size_t bytes);
+void mod_host_free(void* p);
+
+/* ---- seam 1: SceneFlowConstructor::construct() minus ROS publishing (scene_flow_constructor.cpp:91-147) ------ */
+/* Host buffers in, host buffers out, synchronous.
+ *  out_points32 : w*h PointXYZVelocity records of 32 bytes {x,y,z,0,vx,vy,vz,0} = PointCloud2.data with
+ *                 point_step 32, row_step 32*w (pcl_point_xyz_velocity.h:8-34).  May be NULL.
+ *  opt_depth    : w*h float, ~depth topic (disparity_image_processor.cpp:105-121).  May be NULL.
+ *  opt_static_flow : w*h*2 float, ~synthetic_optical_flow (scene_flow_constructor.cpp:65-89).  May be NULL.
+ * Degrade rules of the reference (scene_flow_constructor.cpp:104-133): the caller must not call this without flow,
+ * previous disparity or transform -- in those cases the reference publishes no scene_flow at all. */
+int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_disparity* now,
+                   const mod_disparity* prev, const float* flow_xy, int32_t flow_step_bytes,
+                   const mod_transform* prev2now, double dt_sec, const mod_sf_params* params, void* out_points32,
+                   float* opt_depth, float* opt_static_flow);
+
+/* ---- seam 2: ClustererNodelet::clustering() + publishMovingObjects() (clusterer_nodelet.cpp:85-95,324-343) --- */
+/*  points32   : w*h 32-byte records (PointCloud2.data of ~scene_flow), host.
+ *  opt_labels : w*h int32, the final cluster_map_ (-1 = NOT_BELONGED_), ids in the reference's order.  May be NULL.
+ *  objs/n_objs: MovingObjectArray.moving_object_array in id order. */
+int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_params* params, int32_t* opt_labels,
+                mod_object* objs, int32_t max_objs, int32_t* n_objs);
+
+/* ---- fused host entry: seam 1 + seam 2 with the cloud staying on the GPU ------------------------------------ */
+/* opt_out_points32 is only copied back when non-NULL (the reference publishes ~scene_flow only when it has
+ * subscribers, scene_flow_constructor.cpp:141-142). */
+int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_disparity* now,
+                 const mod_disparity* prev, const float* flow_xy, int32_t flow_step_bytes,
+                 const mod_transform* prev2now, double dt_sec, const mod_sf_params* sf_params,
+                 const mod_cl_params* cl_params, void* opt_out_points32, int32_t* opt_labels, mod_object* objs,
+                 int32_t max_objs, int32_t* n_objs);
+
+/* ---- device-resident batched path (benchmark / multi-frame drivers) ----------------------------------------- */
+/* All d_* pointers are device memory; `stream` is a cudaStream_t (NULL = the context's own stream).  The calls are
+ * ASYNCHRONOUS on that stream and do not synchronise the host.
+ *  d_points32 : batch * frame_stride_points records of 32 bytes (frame_stride_points >= w*h).
+ *  d_mask     : batch * w*h bytes, the clusterer's dynamic_map_ (|v| >= dynamic_speed), fused into the same kernel.
+ *               May be NULL (then no mask is produced and dynamic_speed is ignored).
+ *  d_opt_depth / d_opt_static_flow : batch * w*h (*2) floats or NULL. */
+int mod_scene_flow_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const mod_camera* cam,
+                               const mod_pair_dev* pairs /* host array[batch] */, const mod_sf_params* params,
+                               double dynamic_speed, void* d_points32, size_t frame_stride_points, uint8_t* d_mask,
+                               float* d_opt_depth, float* d_opt_static_flow);
+
+/*  d_mask       : batch * w*h bytes as written by mod_scene_flow_batched_dev, or NULL to derive it from the cloud
+ *                 (calculateDynamicMap, clusterer_nodelet.cpp:40-54).
+ *  d_opt_labels : batch * w*h int32 or NULL.
+ *  d_objs       : batch * max_objs records; d_stats: batch records (n_objects, status per frame). */
+int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const void* d_points32,
+                            size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params* params,
+                            int32_t* d_opt_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats);
+
+/* ---- host batched streaming path (end-to-end: H2D + kernels + D2H inside the call) --------------------------- */
+/* A sequence of n_frames disparity images (host, dense, preferably pinned) forms n_frames-1 frame pairs:
+ * pair i = (prev = frame i, now = frame i+1), flows[i] and transforms[i]/dt[i] belong to pair i.
+ * Each disparity frame is uploaded once; uploads, kernels and downloads of successive pairs overlap on separate
+ * streams.  opt_out_points32 (n_pairs * w*h*32 bytes) is downloaded only when non-NULL. */
+int mod_pipeline_sequence_host(mod_ctx* ctx, int w, int h, int n_frames, const mod_camera* cam, float f, float T,
+                               float min_disparity, float max_disparity, const float* disp_frames,
+                               const float* flows, const mod_transform* transforms, const double* dt_sec,
+                               const mod_sf_params* sf_params, const mod_cl_params* cl_params,
+                               void* opt_out_points32, mod_object* objs, int32_t max_objs_per_pair,
+                               mod_frame_stats* stats /* host array[n_frames-1] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOD_B200_H_ */

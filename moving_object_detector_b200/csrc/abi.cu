@@ -1,0 +1,633 @@
+// abi.cu -- the C ABI of include/mod_b200.h: context, workspaces, host<->device staging and kernel sequencing.
+// No computation happens on the host except O(1) parameter preparation (quaternion -> rotation matrix in the
+// reference's order of operations, float equivalents of the double thresholds).
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mod {
+
+float float_ceil_of_double(double th) {
+  float f = static_cast<float>(th);
+  if (static_cast<double>(f) < th) f = nextafterf(f, INFINITY);
+  return f;
+}
+float float_floor_of_double(double th) {
+  float f = static_cast<float>(th);
+  if (static_cast<double>(f) > th) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
+}  // namespace mod
+
+using namespace mod;
+
+struct mod_ctx {
+  int device = 0;
+  int max_w = 0, max_h = 0, max_batch = 0, max_clusters = 0;
+  size_t maxP = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  char err[512] = {0};
+
+  // ray look-up tables (projectPixelTo3dRay), cached per camera / size
+  double* d_ray = nullptr;
+  mod_camera lut_cam{};
+  int lut_w = 0, lut_h = 0;
+
+  // clusterer workspaces (max_batch frames)
+  int* d_parent = nullptr;
+  int* d_count = nullptr;
+  int* d_slot = nullptr;
+  uint8_t* d_flags = nullptr;
+  float* d_speed = nullptr;
+  uint32_t* d_member_speed = nullptr;
+  int* d_member_pixel = nullptr;
+  int* d_frame_ints = nullptr;  // n_slots[max_batch], n_dynamic[max_batch]
+  int* d_work = nullptr;        // work_count, work_cursor
+  ClusterStat* d_stats = nullptr;
+  int2* d_work_items = nullptr;
+  int* d_member_offset = nullptr;
+  int* d_cursor = nullptr;
+  uint8_t* d_mask_own = nullptr;  // mask derived from a cloud when the caller has none (max_batch frames)
+
+  // single-frame staging for the host seams (lazily allocated)
+  bool host_ready = false;
+  float* d_disp_now = nullptr;
+  float* d_disp_prev = nullptr;
+  float* d_flow = nullptr;
+  float* d_points = nullptr;
+  uint8_t* d_mask = nullptr;
+  int32_t* d_labels = nullptr;
+  float* d_depth = nullptr;
+  float* d_static = nullptr;
+  mod_object* d_objs = nullptr;
+  mod_frame_stats* d_fstats = nullptr;
+  mod_frame_stats* h_fstats = nullptr;  // pinned
+
+  // streaming buffers of mod_pipeline_sequence_host (lazily allocated)
+  struct SeqBuf {
+    float* d_disp = nullptr;   // (chunk + 1) frames
+    float* d_flow = nullptr;   // chunk pairs
+    float* d_points = nullptr; // chunk pairs
+    uint8_t* d_mask = nullptr;
+    mod_object* d_objs = nullptr;
+    mod_frame_stats* d_stats = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+    int max_objs = 0;
+  };
+  int seq_chunk = 0;
+  SeqBuf seq[2];
+};
+
+namespace {
+
+int fail(mod_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define MOD_CK(ctx, call)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t e__ = (call);                                                                               \
+    if (e__ != cudaSuccess)                                                                                 \
+      return fail((ctx), MOD_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+// tf2::transformToEigen + Quaterniond::toRotationMatrix (Eigen 3.3 order of operations).
+// O(1) host-side parameter preparation; IEEE double on the host equals what the reference's host computes.
+void fill_transform(const mod_transform& m, SfPair& p) {
+  const double x = m.qx, y = m.qy, z = m.qz, w = m.qw;
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  p.R[0] = 1.0 - (tyy + tzz);
+  p.R[1] = txy - twz;
+  p.R[2] = txz + twy;
+  p.R[3] = txy + twz;
+  p.R[4] = 1.0 - (txx + tzz);
+  p.R[5] = tyz - twx;
+  p.R[6] = txz - twy;
+  p.R[7] = tyz + twx;
+  p.R[8] = 1.0 - (txx + tyy);
+  p.t[0] = m.tx;
+  p.t[1] = m.ty;
+  p.t[2] = m.tz;
+}
+
+bool same_camera(const mod_camera& a, const mod_camera& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
+
+int ensure_lut(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_camera& cam) {
+  if (ctx->lut_w == w && ctx->lut_h == h && same_camera(ctx->lut_cam, cam)) return MOD_OK;
+  launch_ray_lut(s, ctx->d_ray, ctx->d_ray + ctx->max_w, w, h, cam);
+  MOD_CK(ctx, cudaGetLastError());
+  ctx->lut_cam = cam;
+  ctx->lut_w = w;
+  ctx->lut_h = h;
+  return MOD_OK;
+}
+
+int check_size(mod_ctx* ctx, int w, int h, int batch) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  if (w <= 0 || h <= 0 || batch <= 0) return fail(ctx, MOD_ERR_INVALID_ARG, "non-positive size %dx%d batch %d", w, h, batch);
+  if (w > ctx->max_w || h > ctx->max_h)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "frame %dx%d exceeds the context's %dx%d", w, h, ctx->max_w, ctx->max_h);
+  if (batch > ctx->max_batch) return fail(ctx, MOD_ERR_INVALID_ARG, "batch %d exceeds the context's %d", batch, ctx->max_batch);
+  return MOD_OK;
+}
+
+// Scene-flow over `batch` device-resident pairs, chunked so the per-pair constants fit the parameter bank.
+int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const mod_camera& cam,
+                       const mod_pair_dev* pairs, const mod_sf_params& params, double dynamic_speed, float* d_points,
+                       size_t frame_stride_points, uint8_t* d_mask, float* d_depth, float* d_static) {
+  int rc = ensure_lut(ctx, s, w, h, cam);
+  if (rc != MOD_OK) return rc;
+  SfLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  L.ray_x = ctx->d_ray;
+  L.ray_y = ctx->d_ray + ctx->max_w;
+  L.fx = cam.fx;
+  L.fy = cam.fy;
+  L.cx = cam.cx;
+  L.cy = cam.cy;
+  L.Tx = cam.Tx;
+  L.Ty = cam.Ty;
+  L.w = w;
+  L.h = h;
+  L.flow_diff_thr = static_cast<float>(params.dynamic_flow_diff);  // float >= int promotes the int (cpp:198)
+  L.speed_thr = float_ceil_of_double(dynamic_speed);
+  L.points = d_points;
+  L.points_frame_stride = frame_stride_points;
+  L.mask = d_mask;
+  L.depth = d_depth;
+  L.static_flow = d_static;
+  for (int first = 0; first < batch; first += kSfMaxPairsPerLaunch) {
+    const int n = (batch - first < kSfMaxPairsPerLaunch) ? batch - first : kSfMaxPairsPerLaunch;
+    for (int k = 0; k < n; k++) {
+      const mod_pair_dev& src = pairs[first + k];
+      SfPair& p = L.pair[k];
+      p.disp_now = src.disp_now;
+      p.disp_prev = src.disp_prev;
+      p.flow = src.flow_xy;
+      fill_transform(src.prev2now, p);
+      p.dt = src.dt_sec;
+      p.fT_now = src.f_now * src.T_now;  // float product, disparity_image_processor.cpp:43
+      p.min_now = src.min_disparity_now;
+      p.max_now = src.max_disparity_now;
+      p.fT_prev = src.f_prev * src.T_prev;
+      p.min_prev = src.min_disparity_prev;
+      p.max_prev = src.max_disparity_prev;
+    }
+    L.first_frame = first;
+    MOD_CK(ctx, launch_scene_flow(s, L, n));
+  }
+  return MOD_OK;
+}
+
+int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const float* d_points,
+                    size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params& params,
+                    int32_t* d_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats) {
+  if (params.cluster_size == 0)
+    return fail(ctx, MOD_ERR_INVALID_PARAM, "cluster_size == 0: the reference throws std::out_of_range "
+                "(cluster.at(0) on an empty cluster, clusterer_nodelet.cpp:174)");
+  if (params.neighbor_distance < 0) return fail(ctx, MOD_ERR_INVALID_PARAM, "neighbor_distance < 0");
+  if (max_objs < 0 || !d_objs || !d_stats) return fail(ctx, MOD_ERR_INVALID_ARG, "objs / stats missing");
+  const size_t P = static_cast<size_t>(w) * h;
+  const float speed_thr = float_ceil_of_double(params.dynamic_speed);
+  if (!d_mask) {
+    MOD_CK(ctx, launch_dynamic_map(s, d_points, frame_stride_points, ctx->d_mask_own, w, h, batch, speed_thr));
+    d_mask = ctx->d_mask_own;
+  }
+  ClLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  L.points = d_points;
+  L.points_frame_stride = frame_stride_points;
+  L.mask = d_mask;
+  L.w = w;
+  L.h = h;
+  L.batch = batch;
+  L.n = params.neighbor_distance;
+  L.depth_thr = float_floor_of_double(params.depth_diff);
+  L.speed_thr = speed_thr;
+  // removeSmallClusters compares size_t < (size_t)cluster_size (cpp:374): a negative threshold removes everything;
+  // components need at least one edge, i.e. two pixels, to be labelled at all.
+  L.min_size = params.cluster_size < 0 ? 0x7fffffff : (params.cluster_size < 2 ? 2 : params.cluster_size);
+  L.max_clusters = ctx->max_clusters;
+  L.max_objs = max_objs;
+  L.parent = ctx->d_parent;
+  L.count = ctx->d_count;
+  L.slot = ctx->d_slot;
+  L.flags = ctx->d_flags;
+  L.speed = ctx->d_speed;
+  L.n_slots = ctx->d_frame_ints;
+  L.n_dynamic = ctx->d_frame_ints + batch;  // adjacent: one reset kernel clears both
+  L.stats = ctx->d_stats;
+  L.labels = d_labels;
+  L.objs = d_objs;
+  L.frame_stats = d_stats;
+  ClExtra X;
+  X.work_count = ctx->d_work;
+  X.work_cursor = ctx->d_work + 1;
+  X.work_items = ctx->d_work_items;
+  X.member_offset = ctx->d_member_offset;
+  X.cursor = ctx->d_cursor;
+  X.member_speed = ctx->d_member_speed;
+  X.member_pixel = ctx->d_member_pixel;
+  (void)P;
+  MOD_CK(ctx, launch_cluster(s, L, X));
+  return MOD_OK;
+}
+
+int ensure_host_staging(mod_ctx* ctx) {
+  if (ctx->host_ready) return MOD_OK;
+  const size_t P = ctx->maxP;
+  MOD_CK(ctx, dev_alloc(&ctx->d_disp_now, P));
+  MOD_CK(ctx, dev_alloc(&ctx->d_disp_prev, P));
+  MOD_CK(ctx, dev_alloc(&ctx->d_flow, P * 2));
+  MOD_CK(ctx, dev_alloc(&ctx->d_points, P * 8));
+  MOD_CK(ctx, dev_alloc(&ctx->d_mask, P));
+  MOD_CK(ctx, dev_alloc(&ctx->d_labels, P));
+  MOD_CK(ctx, dev_alloc(&ctx->d_depth, P));
+  MOD_CK(ctx, dev_alloc(&ctx->d_static, P * 2));
+  MOD_CK(ctx, dev_alloc(&ctx->d_objs, static_cast<size_t>(ctx->max_clusters)));
+  MOD_CK(ctx, dev_alloc(&ctx->d_fstats, 1));
+  MOD_CK(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_fstats), sizeof(mod_frame_stats)));
+  ctx->host_ready = true;
+  return MOD_OK;
+}
+
+int upload_image(mod_ctx* ctx, cudaStream_t s, float* dst, const float* src, int step_bytes, int w, int h,
+                 int channels) {
+  const size_t row = static_cast<size_t>(w) * channels * sizeof(float);
+  if (static_cast<size_t>(step_bytes) < row) return fail(ctx, MOD_ERR_INVALID_ARG, "row step %d smaller than a row", step_bytes);
+  MOD_CK(ctx, cudaMemcpy2DAsync(dst, row, src, static_cast<size_t>(step_bytes), row, h, cudaMemcpyHostToDevice, s));
+  return MOD_OK;
+}
+
+mod_pair_dev make_pair(const float* d_now, const float* d_prev, const float* d_flow, const mod_disparity& now,
+                       const mod_disparity& prev, const mod_transform& T, double dt) {
+  mod_pair_dev p;
+  std::memset(&p, 0, sizeof(p));
+  p.disp_now = d_now;
+  p.disp_prev = d_prev;
+  p.flow_xy = d_flow;
+  p.f_now = now.f;
+  p.T_now = now.T;
+  p.min_disparity_now = now.min_disparity;
+  p.max_disparity_now = now.max_disparity;
+  p.f_prev = prev.f;
+  p.T_prev = prev.T;
+  p.min_disparity_prev = prev.min_disparity;
+  p.max_disparity_prev = prev.max_disparity;
+  p.prev2now = T;
+  p.dt_sec = dt;
+  return p;
+}
+
+// Downloads objects + stats of one frame and converts the per-frame status into the return code.
+int fetch_objects(mod_ctx* ctx, cudaStream_t s, mod_object* objs, int32_t max_objs, int32_t* n_objs) {
+  MOD_CK(ctx, cudaMemcpyAsync(ctx->h_fstats, ctx->d_fstats, sizeof(mod_frame_stats), cudaMemcpyDeviceToHost, s));
+  MOD_CK(ctx, cudaStreamSynchronize(s));
+  const mod_frame_stats fs = *ctx->h_fstats;
+  if (n_objs) *n_objs = fs.n_objects;
+  const int n_copy = fs.n_objects < max_objs ? fs.n_objects : max_objs;
+  if (n_copy > 0 && objs)
+    MOD_CK(ctx, cudaMemcpy(objs, ctx->d_objs, static_cast<size_t>(n_copy) * sizeof(mod_object), cudaMemcpyDeviceToHost));
+  if (fs.status == MOD_ERR_CLUSTER_SLOTS)
+    return fail(ctx, MOD_ERR_CLUSTER_SLOTS, "more than %d surviving clusters in one frame", ctx->max_clusters);
+  if (fs.status == MOD_ERR_CAPACITY) return fail(ctx, MOD_ERR_CAPACITY, "%d objects > max_objs %d", fs.n_objects, max_objs);
+  return MOD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mod_abi_version(void) { return MOD_B200_ABI_VERSION; }
+
+void* mod_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void mod_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {
+  if (!out_ctx) return MOD_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  if (max_w <= 0 || max_h <= 0 || max_batch <= 0 || max_clusters < 0) return MOD_ERR_INVALID_ARG;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return MOD_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MOD_ERR_NO_DEVICE;
+  if (prop.major != 10) return MOD_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return MOD_ERR_NO_DEVICE;
+
+  mod_ctx* ctx = new (std::nothrow) mod_ctx();
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  ctx->device = device;
+  ctx->max_w = max_w;
+  ctx->max_h = max_h;
+  ctx->max_batch = max_batch;
+  ctx->max_clusters = max_clusters == 0 ? 4096 : (max_clusters > 8192 ? 8192 : max_clusters);
+  ctx->maxP = static_cast<size_t>(max_w) * max_h;
+  const size_t N = ctx->maxP * max_batch;
+  const size_t C = static_cast<size_t>(ctx->max_clusters) * max_batch;
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t r) {
+    if (e == cudaSuccess) e = r;
+  };
+  ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  ok(dev_alloc(&ctx->d_ray, static_cast<size_t>(max_w) + max_h));
+  ok(dev_alloc(&ctx->d_parent, N));
+  ok(dev_alloc(&ctx->d_count, N));
+  ok(dev_alloc(&ctx->d_slot, N));
+  ok(dev_alloc(&ctx->d_flags, N));
+  ok(dev_alloc(&ctx->d_speed, N));
+  ok(dev_alloc(&ctx->d_member_speed, N));
+  ok(dev_alloc(&ctx->d_member_pixel, N));
+  ok(dev_alloc(&ctx->d_mask_own, N));
+  ok(dev_alloc(&ctx->d_frame_ints, static_cast<size_t>(2) * max_batch));
+  ok(dev_alloc(&ctx->d_work, 2));
+  ok(dev_alloc(&ctx->d_stats, C));
+  ok(dev_alloc(&ctx->d_work_items, C));
+  ok(dev_alloc(&ctx->d_member_offset, C));
+  ok(dev_alloc(&ctx->d_cursor, C));
+  if (e != cudaSuccess) {
+    mod_destroy(ctx);
+    return MOD_ERR_CUDA;
+  }
+  *out_ctx = ctx;
+  return MOD_OK;
+}
+
+void mod_destroy(mod_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  cudaFree(ctx->d_ray);
+  cudaFree(ctx->d_parent);
+  cudaFree(ctx->d_count);
+  cudaFree(ctx->d_slot);
+  cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_speed);
+  cudaFree(ctx->d_member_speed);
+  cudaFree(ctx->d_member_pixel);
+  cudaFree(ctx->d_mask_own);
+  cudaFree(ctx->d_frame_ints);
+  cudaFree(ctx->d_work);
+  cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_work_items);
+  cudaFree(ctx->d_member_offset);
+  cudaFree(ctx->d_cursor);
+  cudaFree(ctx->d_disp_now);
+  cudaFree(ctx->d_disp_prev);
+  cudaFree(ctx->d_flow);
+  cudaFree(ctx->d_points);
+  cudaFree(ctx->d_mask);
+  cudaFree(ctx->d_labels);
+  cudaFree(ctx->d_depth);
+  cudaFree(ctx->d_static);
+  cudaFree(ctx->d_objs);
+  cudaFree(ctx->d_fstats);
+  if (ctx->h_fstats) cudaFreeHost(ctx->h_fstats);
+  for (auto& b : ctx->seq) {
+    cudaFree(b.d_disp);
+    cudaFree(b.d_flow);
+    cudaFree(b.d_points);
+    cudaFree(b.d_mask);
+    cudaFree(b.d_objs);
+    cudaFree(b.d_stats);
+    if (b.ev_in) cudaEventDestroy(b.ev_in);
+    if (b.ev_comp) cudaEventDestroy(b.ev_comp);
+    if (b.ev_out) cudaEventDestroy(b.ev_out);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  delete ctx;
+}
+
+int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_disparity* now,
+                   const mod_disparity* prev, const float* flow_xy, int32_t flow_step_bytes,
+                   const mod_transform* prev2now, double dt_sec, const mod_sf_params* params, void* out_points32,
+                   float* opt_depth, float* opt_static_flow) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!cam || !now || !prev || !now->data || !prev->data || !flow_xy || !prev2now || !params)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  const size_t P = static_cast<size_t>(w) * h;
+  if ((rc = upload_image(ctx, s, ctx->d_disp_now, now->data, now->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  if ((rc = upload_image(ctx, s, ctx->d_disp_prev, prev->data, prev->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  if ((rc = upload_image(ctx, s, ctx->d_flow, flow_xy, flow_step_bytes, w, h, 2)) != MOD_OK) return rc;
+  const mod_pair_dev pair = make_pair(ctx->d_disp_now, ctx->d_disp_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
+  rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *params, 0.0, ctx->d_points, P, nullptr,
+                          opt_depth ? ctx->d_depth : nullptr, opt_static_flow ? ctx->d_static : nullptr);
+  if (rc != MOD_OK) return rc;
+  if (out_points32) MOD_CK(ctx, cudaMemcpyAsync(out_points32, ctx->d_points, P * 32, cudaMemcpyDeviceToHost, s));
+  if (opt_depth) MOD_CK(ctx, cudaMemcpyAsync(opt_depth, ctx->d_depth, P * 4, cudaMemcpyDeviceToHost, s));
+  if (opt_static_flow) MOD_CK(ctx, cudaMemcpyAsync(opt_static_flow, ctx->d_static, P * 8, cudaMemcpyDeviceToHost, s));
+  MOD_CK(ctx, cudaStreamSynchronize(s));
+  return MOD_OK;
+}
+
+int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_params* params, int32_t* opt_labels,
+                mod_object* objs, int32_t max_objs, int32_t* n_objs) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!points32 || !params || max_objs < 0 || (max_objs > 0 && !objs)) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  const size_t P = static_cast<size_t>(w) * h;
+  MOD_CK(ctx, cudaMemcpyAsync(ctx->d_points, points32, P * 32, cudaMemcpyHostToDevice, s));
+  const int32_t cap = max_objs < ctx->max_clusters ? max_objs : ctx->max_clusters;
+  rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, nullptr, *params, opt_labels ? ctx->d_labels : nullptr,
+                       ctx->d_objs, cap, ctx->d_fstats);
+  if (rc != MOD_OK) return rc;
+  if (opt_labels) MOD_CK(ctx, cudaMemcpyAsync(opt_labels, ctx->d_labels, P * 4, cudaMemcpyDeviceToHost, s));
+  return fetch_objects(ctx, s, objs, cap, n_objs);
+}
+
+int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_disparity* now,
+                 const mod_disparity* prev, const float* flow_xy, int32_t flow_step_bytes,
+                 const mod_transform* prev2now, double dt_sec, const mod_sf_params* sf_params,
+                 const mod_cl_params* cl_params, void* opt_out_points32, int32_t* opt_labels, mod_object* objs,
+                 int32_t max_objs, int32_t* n_objs) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!cam || !now || !prev || !now->data || !prev->data || !flow_xy || !prev2now || !sf_params || !cl_params ||
+      max_objs < 0 || (max_objs > 0 && !objs))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
+  cudaStream_t s = ctx->stream;
+  const size_t P = static_cast<size_t>(w) * h;
+  if ((rc = upload_image(ctx, s, ctx->d_disp_now, now->data, now->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  if ((rc = upload_image(ctx, s, ctx->d_disp_prev, prev->data, prev->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  if ((rc = upload_image(ctx, s, ctx->d_flow, flow_xy, flow_step_bytes, w, h, 2)) != MOD_OK) return rc;
+  const mod_pair_dev pair = make_pair(ctx->d_disp_now, ctx->d_disp_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
+  rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *sf_params, cl_params->dynamic_speed, ctx->d_points, P,
+                          ctx->d_mask, nullptr, nullptr);
+  if (rc != MOD_OK) return rc;
+  const int32_t cap = max_objs < ctx->max_clusters ? max_objs : ctx->max_clusters;
+  rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, ctx->d_mask, *cl_params,
+                       opt_labels ? ctx->d_labels : nullptr, ctx->d_objs, cap, ctx->d_fstats);
+  if (rc != MOD_OK) return rc;
+  if (opt_out_points32) MOD_CK(ctx, cudaMemcpyAsync(opt_out_points32, ctx->d_points, P * 32, cudaMemcpyDeviceToHost, s));
+  if (opt_labels) MOD_CK(ctx, cudaMemcpyAsync(opt_labels, ctx->d_labels, P * 4, cudaMemcpyDeviceToHost, s));
+  return fetch_objects(ctx, s, objs, cap, n_objs);
+}
+
+int mod_scene_flow_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const mod_camera* cam,
+                               const mod_pair_dev* pairs, const mod_sf_params* params, double dynamic_speed,
+                               void* d_points32, size_t frame_stride_points, uint8_t* d_mask, float* d_opt_depth,
+                               float* d_opt_static_flow) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  if (w <= 0 || h <= 0 || batch <= 0 || w > ctx->max_w || h > ctx->max_h)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "bad size %dx%d batch %d", w, h, batch);
+  if (!cam || !pairs || !params || !d_points32 || frame_stride_points < static_cast<size_t>(w) * h)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "null argument or frame stride smaller than a frame");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  return run_scene_flow_dev(ctx, s, w, h, batch, *cam, pairs, *params, dynamic_speed, static_cast<float*>(d_points32),
+                            frame_stride_points, d_mask, d_opt_depth, d_opt_static_flow);
+}
+
+int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const void* d_points32,
+                            size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params* params,
+                            int32_t* d_opt_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats) {
+  int rc = check_size(ctx, w, h, batch);
+  if (rc != MOD_OK) return rc;
+  if (!d_points32 || !params || frame_stride_points < static_cast<size_t>(w) * h)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "null argument or frame stride smaller than a frame");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  return run_cluster_dev(ctx, s, w, h, batch, static_cast<const float*>(d_points32), frame_stride_points, d_mask,
+                         *params, d_opt_labels, d_objs, max_objs, d_stats);
+}
+
+int mod_pipeline_sequence_host(mod_ctx* ctx, int w, int h, int n_frames, const mod_camera* cam, float f, float T,
+                               float min_disparity, float max_disparity, const float* disp_frames,
+                               const float* flows, const mod_transform* transforms, const double* dt_sec,
+                               const mod_sf_params* sf_params, const mod_cl_params* cl_params,
+                               void* opt_out_points32, mod_object* objs, int32_t max_objs_per_pair,
+                               mod_frame_stats* stats) {
+  const int n_pairs = n_frames - 1;
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  if (n_pairs <= 0) return fail(ctx, MOD_ERR_INVALID_ARG, "need at least two frames");
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!cam || !disp_frames || !flows || !transforms || !dt_sec || !sf_params || !cl_params || !objs || !stats ||
+      max_objs_per_pair <= 0)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t P = static_cast<size_t>(w) * h;
+
+  // chunk = as many pairs as the clusterer workspace holds, at most 8: large enough to amortise launches,
+  // small enough that upload / compute / download of neighbouring chunks overlap.
+  int chunk = ctx->max_batch < 8 ? ctx->max_batch : 8;
+  if (ctx->seq_chunk == 0) {
+    for (auto& b : ctx->seq) {
+      MOD_CK(ctx, dev_alloc(&b.d_disp, ctx->maxP * (chunk + 1)));
+      MOD_CK(ctx, dev_alloc(&b.d_flow, ctx->maxP * 2 * chunk));
+      MOD_CK(ctx, dev_alloc(&b.d_points, ctx->maxP * 8 * chunk));
+      MOD_CK(ctx, dev_alloc(&b.d_mask, ctx->maxP * chunk));
+      MOD_CK(ctx, dev_alloc(&b.d_stats, static_cast<size_t>(chunk)));
+      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_in, cudaEventDisableTiming));
+      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_comp, cudaEventDisableTiming));
+      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_out, cudaEventDisableTiming));
+    }
+    ctx->seq_chunk = chunk;
+  }
+  chunk = ctx->seq_chunk;
+  for (auto& b : ctx->seq) {
+    if (b.max_objs < max_objs_per_pair) {
+      cudaFree(b.d_objs);
+      b.d_objs = nullptr;
+      MOD_CK(ctx, dev_alloc(&b.d_objs, static_cast<size_t>(chunk) * max_objs_per_pair));
+      b.max_objs = max_objs_per_pair;
+    }
+  }
+
+  mod_disparity meta{f, T, min_disparity, max_disparity, nullptr, 0};
+  std::vector<mod_pair_dev> pairs(chunk);
+  int n_chunks = (n_pairs + chunk - 1) / chunk;
+  for (int c = 0; c < n_chunks; c++) {
+    mod_ctx::SeqBuf& b = ctx->seq[c & 1];
+    const int first = c * chunk;
+    const int n = (n_pairs - first < chunk) ? n_pairs - first : chunk;
+    // the buffer is free once its previous download (chunk c-2) finished
+    if (c >= 2) MOD_CK(ctx, cudaStreamWaitEvent(ctx->s_in, b.ev_out, 0));
+    // slot 0 = frame `first`: uploaded for chunk 0, otherwise carried device-to-device from the previous chunk's
+    // last slot.  The carry runs on the upload stream, i.e. after the previous chunk's upload and before the
+    // next upload into that buffer, so no extra event is needed.
+    if (c == 0) {
+      MOD_CK(ctx, cudaMemcpyAsync(b.d_disp, disp_frames, P * 4, cudaMemcpyHostToDevice, ctx->s_in));
+    } else {
+      mod_ctx::SeqBuf& pb = ctx->seq[(c - 1) & 1];
+      MOD_CK(ctx, cudaMemcpyAsync(b.d_disp, pb.d_disp + P * chunk, P * 4, cudaMemcpyDeviceToDevice, ctx->s_in));
+    }
+    // frames first+1 .. first+n go to slots 1..n
+    MOD_CK(ctx, cudaMemcpyAsync(b.d_disp + P, disp_frames + P * (first + 1), P * 4 * n, cudaMemcpyHostToDevice, ctx->s_in));
+    MOD_CK(ctx, cudaMemcpyAsync(b.d_flow, flows + P * 2 * first, P * 8 * n, cudaMemcpyHostToDevice, ctx->s_in));
+    MOD_CK(ctx, cudaEventRecord(b.ev_in, ctx->s_in));
+
+    MOD_CK(ctx, cudaStreamWaitEvent(ctx->stream, b.ev_in, 0));
+    for (int k = 0; k < n; k++)
+      pairs[k] = make_pair(b.d_disp + P * (k + 1), b.d_disp + P * k, b.d_flow + P * 2 * k, meta, meta,
+                           transforms[first + k], dt_sec[first + k]);
+    rc = run_scene_flow_dev(ctx, ctx->stream, w, h, n, *cam, pairs.data(), *sf_params, cl_params->dynamic_speed,
+                            b.d_points, P, b.d_mask, nullptr, nullptr);
+    if (rc != MOD_OK) return rc;
+    rc = run_cluster_dev(ctx, ctx->stream, w, h, n, b.d_points, P, b.d_mask, *cl_params, nullptr, b.d_objs,
+                         max_objs_per_pair, b.d_stats);
+    if (rc != MOD_OK) return rc;
+    MOD_CK(ctx, cudaEventRecord(b.ev_comp, ctx->stream));
+
+    MOD_CK(ctx, cudaStreamWaitEvent(ctx->s_out, b.ev_comp, 0));
+    if (opt_out_points32)
+      MOD_CK(ctx, cudaMemcpyAsync(static_cast<char*>(opt_out_points32) + P * 32 * first, b.d_points, P * 32 * n,
+                                  cudaMemcpyDeviceToHost, ctx->s_out));
+    MOD_CK(ctx, cudaMemcpyAsync(objs + static_cast<size_t>(first) * max_objs_per_pair, b.d_objs,
+                                sizeof(mod_object) * static_cast<size_t>(n) * max_objs_per_pair, cudaMemcpyDeviceToHost,
+                                ctx->s_out));
+    MOD_CK(ctx, cudaMemcpyAsync(stats + first, b.d_stats, sizeof(mod_frame_stats) * n, cudaMemcpyDeviceToHost, ctx->s_out));
+    MOD_CK(ctx, cudaEventRecord(b.ev_out, ctx->s_out));
+  }
+  MOD_CK(ctx, cudaStreamSynchronize(ctx->s_out));
+  MOD_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  int worst = MOD_OK;
+  for (int i = 0; i < n_pairs; i++)
+    if (stats[i].status != MOD_OK && worst == MOD_OK) worst = stats[i].status;
+  if (worst != MOD_OK) return fail(ctx, worst, "a frame reported status %d", worst);
+  return MOD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// common.cuh -- shared declarations of the sm_100a kernels behind include/mod_b200.h
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mod_b200.h"
+
+namespace mod {
+
+// ---------------------------------------------------------------------------------------------------------
+// Scene-flow launch descriptor.  It is passed BY VALUE as a __grid_constant__ kernel parameter, so the per-pair
+// ego-motion transforms, timestamps and disparity scalars live in the constant bank (no global loads, no
+// cudaMemcpyToSymbol ordering hazards, CUDA-graph friendly).
+// ---------------------------------------------------------------------------------------------------------
+struct SfPair {
+  const float* disp_now;   // dense 32FC1, device
+  const float* disp_prev;  // dense 32FC1, device
+  const float* flow;       // dense 32FC2, device
+  double R[9];             // row-major rotation, Eigen::Quaterniond::toRotationMatrix order of operations
+  double t[3];
+  double dt;               // (stamp_now - stamp_prev).toSec()
+  float fT_now, min_now, max_now;     // f*T evaluated in float as at disparity_image_processor.cpp:43
+  float fT_prev, min_prev, max_prev;
+};
+
+constexpr int kSfMaxPairsPerLaunch = 48;  // 48 * 160 B = 7.5 KB of the 32 KB parameter space
+
+struct SfLaunch {
+  SfPair pair[kSfMaxPairsPerLaunch];
+  const double* ray_x;  // [w]  ((double)u - cx - Tx) / fx   (PinholeCameraModel::projectPixelTo3dRay)
+  const double* ray_y;  // [h]  ((double)v - cy - Ty) / fy
+  double fx, fy, cx, cy, Tx, Ty;
+  int w, h;
+  float flow_diff_thr;   // (float)dynamic_flow_diff
+  float speed_thr;       // smallest float >= dynamic_speed   ((double)a >= th  <=>  a >= th_up)
+  float* points;         // 8 floats per point
+  size_t points_frame_stride;  // in points
+  uint8_t* mask;         // may be null
+  float* depth;          // may be null
+  float* static_flow;    // may be null
+  int first_frame;       // output frame index of pair[0]
+};
+
+// Clusterer launch descriptor (one per batched call; every kernel grid-strides over the batch's flat pixel range).
+struct ClLaunch {
+  const float* points;   // 8 floats per point
+  size_t points_frame_stride;  // in points
+  const uint8_t* mask;   // dynamic map, 1 byte per pixel, dense per frame
+  int w, h, batch;
+  int n;                 // neighbor_distance
+  float depth_thr;       // largest float <= depth_diff   ((double)a > th  <=>  a > th_down)
+  float speed_thr;       // smallest float >= dynamic_speed
+  int min_size;          // max(cluster_size, 2): isolated dynamic pixels never get a label in the reference
+  int max_clusters;      // survivor slots per frame
+  int max_objs;
+  // per-pixel workspaces, batch * w*h
+  int* parent;
+  int* count;            // component size, valid at roots
+  int* slot;             // survivor slot, valid at roots (-1 = removed)
+  uint8_t* flags;        // bit0: pixel has an accepted up-left neighbour
+  float* speed;          // |v| of survivor members
+  // per-frame workspaces
+  int* n_slots;          // [batch]
+  int* n_dynamic;        // [batch]
+  struct ClusterStat* stats;   // [batch * max_clusters]
+  // outputs
+  int32_t* labels;       // may be null
+  mod_object* objs;
+  mod_frame_stats* frame_stats;
+};
+
+struct ClusterStat {
+  int root;          // pixel index of the union-find root
+  int count;         // number of member pixels
+  int key;           // min raster index of a member that has an accepted up-left neighbour (reference label order)
+  int rank;          // final cluster id (rank of key among the frame's survivors)
+  uint32_t mn[3];    // order-preserving encodings of float min x,y,z
+  uint32_t mx[3];
+  uint32_t sel_prefix;  // radix-select state: bits of the k-th largest speed decided so far
+  uint32_t sel_k;       // remaining rank inside the current prefix bucket (0-based, counted from the largest)
+  int median_idx;       // pixel index whose speed equals the selected value (smallest index among ties)
+  int pad;
+};
+
+void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, int w, int h, const mod_camera& cam);
+cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs);
+cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame_stride_points, uint8_t* mask, int w,
+                               int h, int batch, float speed_thr);
+// Workspaces of the clusterer that are not indexed per pixel in ClLaunch.
+struct ClExtra {
+  int* work_count;         // [1]   (work_cursor must follow it directly)
+  int* work_cursor;        // [1]
+  int2* work_items;        // [batch * max_clusters]  (frame, slot) of every surviving cluster
+  int* member_offset;      // [batch * max_clusters]  start of the cluster's member list inside its frame
+  int* cursor;             // [batch * max_clusters]  fill level of the member list
+  uint32_t* member_speed;  // [batch * w*h]
+  int* member_pixel;       // [batch * w*h]
+};
+cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X);
+
+// float threshold equivalents of the reference's float-vs-double comparisons
+float float_ceil_of_double(double th);   // smallest float >= th
+float float_floor_of_double(double th);  // largest float <= th
+
+}  // namespace mod

@@ -1,0 +1,107 @@
+/*
+ * mod_oracle.h -- C interface of the CPU ORACLE for the scene-flow / clusterer hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under moving_object_detector_b200/ (the product) may include,
+ * link or call this.  Allowed users: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline /
+ * --impl reference legs (as the checker / the timed CPU baseline, never as the shipped path).
+ *
+ * PARITY STATUS: *unpinned*.  The reference (ROS Melodic + PCL + Eigen + OpenCV) cannot be compiled in
+ * this image and ships no tests, golden vectors or fixtures.  This oracle is a
+ * line-against-line restatement of the cited reference loops; the only piece validated against real
+ * reference code is the label-equivalence table (oracle/_ref, built from
+ * /root/reference/scene_flow_clusterer/src/lookup_table.cpp by oracle/Makefile).
+ *
+ * The struct layouts deliberately equal those in include/mod_b200.h so that a test can hand the same
+ * ctypes buffers to both sides, but the two headers share no code.
+ */
+#ifndef MOD_ORACLE_H_
+#define MOD_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* left CameraInfo P[0],P[5],P[2],P[6],P[3],P[7]  (image_geometry::PinholeCameraModel fx() fy() cx() cy() Tx() Ty()) */
+typedef struct { double fx, fy, cx, cy, Tx, Ty; } orc_camera;
+
+/* stereo_msgs/DisparityImage: scalars are float32 on the wire; image is 32FC1 with a byte row stride */
+typedef struct {
+  float f, T, min_disparity, max_disparity;
+  const float* data;
+  int32_t step_bytes;
+} orc_disparity;
+
+/* geometry_msgs/Transform, exactly as stored at scene_flow_constructor.cpp:248-249 */
+typedef struct { double tx, ty, tz, qx, qy, qz, qw; } orc_transform;
+
+/* moving_object_msgs/MovingObject content (the reference computes all of it in float, then widens) */
+typedef struct {
+  int32_t id;
+  float center[3];
+  float velocity[3];
+  float bbox[3];
+  int32_t n_points;
+} orc_object;
+
+/* per-pixel class of the constructVelocityPC state machine */
+enum { ORC_CLASS_NAN = 0,      /* I   : all six fields NaN                          */
+       ORC_CLASS_XYZ_ONLY = 1, /* II  : xyz valid, velocity NaN                     */
+       ORC_CLASS_STATIC = 2,   /* III : xyz valid, velocity = 0                     */
+       ORC_CLASS_MOVING = 3 }; /* IV  : xyz valid, velocity = (now - prev) / dt     */
+
+/* bits of the optional near-threshold side channel */
+enum { ORC_NEAR_FLOW_DIFF = 1,  /* |flow - static_flow| within 1 float ulp of dynamic_flow_diff */
+       ORC_NEAR_SPEED = 2 };    /* |v| within 1 float ulp of dynamic_speed                       */
+
+/*
+ * SceneFlowConstructor::construct() minus ROS publishing (scene_flow_constructor.cpp:91-147).
+ * out_points32: w*h records of 8 floats {x,y,z,0,vx,vy,vz,0} (PointXYZVelocity, PointCloud2.data compatible).
+ * opt_depth (w*h), opt_static_flow (w*h*2), opt_class (w*h) may be NULL.
+ * Returns 0, or <0 on bad arguments.
+ */
+int orc_scene_flow(int w, int h, const orc_camera* cam, const orc_disparity* now, const orc_disparity* prev,
+                   const float* flow_xy, int32_t flow_step_bytes, const orc_transform* prev2now, double dt_sec,
+                   int32_t dynamic_flow_diff, float* out_points32, float* opt_depth, float* opt_static_flow,
+                   uint8_t* opt_class);
+
+/*
+ * ClustererNodelet::clustering() + publishMovingObjects() (clusterer_nodelet.cpp:85-95,324-343).
+ * opt_dynamic_map (w*h, 0/1), opt_labels (w*h, -1 = none), opt_near (w*h) may be NULL.
+ * Returns 0; -2 if more than max_objs objects were produced (n_objs then holds the true count).
+ */
+int orc_cluster(int w, int h, const float* points32, int32_t cluster_size, double depth_diff, double dynamic_speed,
+                int32_t neighbor_distance, uint8_t* opt_dynamic_map, int32_t* opt_labels, uint8_t* opt_near,
+                orc_object* objs, int32_t max_objs, int32_t* n_objs);
+
+/* near-threshold flags for the constructor's 2-D residual gate; same inputs as orc_scene_flow */
+int orc_scene_flow_near(int w, int h, const orc_camera* cam, const orc_disparity* now, const orc_disparity* prev,
+                        const float* flow_xy, int32_t flow_step_bytes, const orc_transform* prev2now,
+                        int32_t dynamic_flow_diff, uint8_t* out_near);
+
+/* quaternion -> 3x3 rotation (row-major, 9 doubles), Eigen::Quaterniond::toRotationMatrix order of operations */
+void orc_quat_to_matrix(const orc_transform* t, double* R9);
+
+/* label-equivalence table, restated (lookup_table.h:10-33); used by the _ref cross-check test.
+ * ops: array of (op, a, b) int triples, op 0 = addLabel, 1 = link(a,b), 2 = lookup(a) -> appended to out. */
+int orc_lookup_table_run(int size, const int32_t* ops, int n_ops, int32_t* out, int max_out);
+
+/*
+ * CPU baseline harness: runs the full reference-structured path (constructor + clusterer) over n_pairs
+ * frame pairs with n_threads std::threads (one pair per thread at a time), repeating `reps` times.
+ * Pair i uses disparity frames prev_index[i] / now_index[i] out of `disp_frames` (n_frames * w * h floats, dense)
+ * and flow pair i (w*h*2 floats, dense), transform i, dt[i].
+ * Returns wall seconds of the best repetition in *best_sec and the total number of objects in *n_objects.
+ */
+int orc_bench_pipeline(int w, int h, const orc_camera* cam, float f, float T, float min_disp, float max_disp,
+                       const float* disp_frames, const int32_t* prev_index, const int32_t* now_index,
+                       const float* flows, const orc_transform* transforms, const double* dt, int n_pairs,
+                       int32_t dynamic_flow_diff, int32_t cluster_size, double depth_diff, double dynamic_speed,
+                       int32_t neighbor_distance, int n_threads, int reps, int stage_mask /*1=constructor,2=clusterer*/,
+                       double* best_sec, int64_t* n_objects);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOD_ORACLE_H_ */
