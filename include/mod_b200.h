@@ -118,6 +118,8 @@ void mod_destroy(mod_ctx* ctx);
 /* Message of the last error on this context ("" if none); valid until the next call on the context. */
 const char* mod_last_error(const mod_ctx* ctx);
 int mod_abi_version(void);
+/* Number of CUDA kernels this context has launched so far (evidence that the GPU path ran; used by bench.py). */
+unsigned long long mod_launch_count(const mod_ctx* ctx);
 
 /* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
 void* mod_host_alloc(size_t bytes);

@@ -142,6 +142,10 @@ class Context:
     def __exit__(self, *exc):
         self.close()
 
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mod_launch_count(self._h))
+
     def _check(self, rc: int, allow=()):
         if rc != _lib.MOD_OK and rc not in allow:
             raise ModError(rc, self._lib.mod_last_error(self._h).decode())

@@ -35,6 +35,7 @@ struct mod_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t s_in = nullptr, s_out = nullptr;
   char err[512] = {0};
+  unsigned long long launches = 0;  // kernels launched by this context (mod_launch_count)
 
   // ray look-up tables (projectPixelTo3dRay), cached per camera / size
   double* d_ray = nullptr;
@@ -138,6 +139,7 @@ int ensure_lut(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_camera& cam
   if (ctx->lut_w == w && ctx->lut_h == h && same_camera(ctx->lut_cam, cam)) return MOD_OK;
   launch_ray_lut(s, ctx->d_ray, ctx->d_ray + ctx->max_w, w, h, cam);
   MOD_CK(ctx, cudaGetLastError());
+  ctx->launches++;
   ctx->lut_cam = cam;
   ctx->lut_w = w;
   ctx->lut_h = h;
@@ -197,6 +199,7 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
     }
     L.first_frame = first;
     MOD_CK(ctx, launch_scene_flow(s, L, n));
+    ctx->launches++;
   }
   return MOD_OK;
 }
@@ -213,6 +216,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   const float speed_thr = float_ceil_of_double(params.dynamic_speed);
   if (!d_mask) {
     MOD_CK(ctx, launch_dynamic_map(s, d_points, frame_stride_points, ctx->d_mask_own, w, h, batch, speed_thr));
+    ctx->launches++;
     d_mask = ctx->d_mask_own;
   }
   ClLaunch L;
@@ -251,7 +255,9 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   X.member_speed = ctx->d_member_speed;
   X.member_pixel = ctx->d_member_pixel;
   (void)P;
-  MOD_CK(ctx, launch_cluster(s, L, X));
+  int n_launches = 0;
+  MOD_CK(ctx, launch_cluster(s, L, X, &n_launches));
+  ctx->launches += n_launches;
   return MOD_OK;
 }
 
@@ -332,6 +338,8 @@ void mod_host_free(void* p) {
 }
 
 const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+unsigned long long mod_launch_count(const mod_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {
   if (!out_ctx) return MOD_ERR_INVALID_ARG;

@@ -473,7 +473,7 @@ __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, si
 
 }  // namespace
 
-cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X) {
+cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, int* n_launches) {
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const size_t total = P * L.batch;
   size_t blocks = (total + kBlock - 1) / kBlock;
@@ -500,6 +500,7 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X) 
   cl_objects_kernel<<<148 * 4, kBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
                                                X.member_speed, X.member_pixel);
   if (L.labels != nullptr) cl_labels_kernel<<<nb, kBlock, 0, s>>>(L);
+  if (n_launches) *n_launches = 9 + (L.labels != nullptr ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -24,7 +24,7 @@ struct SfPair {
   float fT_prev, min_prev, max_prev;
 };
 
-constexpr int kSfMaxPairsPerLaunch = 48;  // 48 * 160 B = 7.5 KB of the 32 KB parameter space
+constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 160 B = 10 KB of the 32 KB parameter space
 
 struct SfLaunch {
   SfPair pair[kSfMaxPairsPerLaunch];
@@ -97,7 +97,8 @@ struct ClExtra {
   uint32_t* member_speed;  // [batch * w*h]
   int* member_pixel;       // [batch * w*h]
 };
-cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X);
+// Returns the number of kernels it launched through *n_launches.
+cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, int* n_launches);
 
 // float threshold equivalents of the reference's float-vs-double comparisons
 float float_ceil_of_double(double th);   // smallest float >= th
