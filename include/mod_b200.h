@@ -120,6 +120,8 @@ const char* mod_last_error(const mod_ctx* ctx);
 int mod_abi_version(void);
 /* Number of CUDA kernels this context has launched so far (evidence that the GPU path ran; used by bench.py). */
 unsigned long long mod_launch_count(const mod_ctx* ctx);
+/* The context's own non-blocking stream (a cudaStream_t), usable as the `stream` argument of the *_dev calls. */
+void* mod_stream(const mod_ctx* ctx);
 
 /* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
 void* mod_host_alloc(size_t bytes);
@@ -155,8 +157,9 @@ int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_di
                  int32_t max_objs, int32_t* n_objs);
 
 /* ---- device-resident batched path (benchmark / multi-frame drivers) ----------------------------------------- */
-/* All d_* pointers are device memory; `stream` is a cudaStream_t (NULL = the context's own stream).  The calls are
- * ASYNCHRONOUS on that stream and do not synchronise the host.
+/* All d_* pointers are device memory; `stream` is a cudaStream_t used as given (NULL = CUDA's legacy default stream,
+ * as in every CUDA API; pass mod_stream(ctx) for the context's own stream).  The calls are ASYNCHRONOUS on that
+ * stream and do not synchronise the host.
  *  d_points32 : batch * frame_stride_points records of 32 bytes (frame_stride_points >= w*h).
  *  d_mask     : batch * w*h bytes, the clusterer's dynamic_map_ (|v| >= dynamic_speed), fused into the same kernel.
  *               May be NULL (then no mask is produced and dynamic_speed is ignored).

@@ -146,6 +146,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.mod_launch_count(self._h))
 
+    @property
+    def stream(self) -> int:
+        """The context's own cudaStream_t as an integer handle."""
+        return int(self._lib.mod_stream(self._h) or 0)
+
     def _check(self, rc: int, allow=()):
         if rc != _lib.MOD_OK and rc not in allow:
             raise ModError(rc, self._lib.mod_last_error(self._h).decode())

@@ -45,13 +45,12 @@ struct mod_ctx {
   // clusterer workspaces (max_batch frames)
   int* d_parent = nullptr;
   int* d_count = nullptr;
-  int* d_slot = nullptr;
   uint8_t* d_flags = nullptr;
-  float* d_speed = nullptr;
+  uint32_t* d_list = nullptr;
   uint32_t* d_member_speed = nullptr;
   int* d_member_pixel = nullptr;
   int* d_frame_ints = nullptr;  // n_slots[max_batch], n_dynamic[max_batch]
-  int* d_work = nullptr;        // work_count, work_cursor
+  int* d_work = nullptr;        // work_count, work_cursor, list_count
   ClusterStat* d_stats = nullptr;
   int2* d_work_items = nullptr;
   int* d_member_offset = nullptr;
@@ -213,6 +212,10 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   if (params.neighbor_distance < 0) return fail(ctx, MOD_ERR_INVALID_PARAM, "neighbor_distance < 0");
   if (max_objs < 0 || !d_objs || !d_stats) return fail(ctx, MOD_ERR_INVALID_ARG, "objs / stats missing");
   const size_t P = static_cast<size_t>(w) * h;
+  if (P * static_cast<size_t>(batch) >= (1ull << 32))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "batch * w * h must stay below 2^32 pixels per call; split the batch");
+  if (d_mask && (reinterpret_cast<uintptr_t>(d_mask) & 15u))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "d_mask must be 16-byte aligned");
   const float speed_thr = float_ceil_of_double(params.dynamic_speed);
   if (!d_mask) {
     MOD_CK(ctx, launch_dynamic_map(s, d_points, frame_stride_points, ctx->d_mask_own, w, h, batch, speed_thr));
@@ -237,9 +240,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   L.max_objs = max_objs;
   L.parent = ctx->d_parent;
   L.count = ctx->d_count;
-  L.slot = ctx->d_slot;
   L.flags = ctx->d_flags;
-  L.speed = ctx->d_speed;
   L.n_slots = ctx->d_frame_ints;
   L.n_dynamic = ctx->d_frame_ints + batch;  // adjacent: one reset kernel clears both
   L.stats = ctx->d_stats;
@@ -249,6 +250,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   ClExtra X;
   X.work_count = ctx->d_work;
   X.work_cursor = ctx->d_work + 1;
+  X.list = ctx->d_list;
   X.work_items = ctx->d_work_items;
   X.member_offset = ctx->d_member_offset;
   X.cursor = ctx->d_cursor;
@@ -341,6 +343,8 @@ const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null c
 
 unsigned long long mod_launch_count(const mod_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+void* mod_stream(const mod_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {
   if (!out_ctx) return MOD_ERR_INVALID_ARG;
   *out_ctx = nullptr;
@@ -372,14 +376,13 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   ok(dev_alloc(&ctx->d_ray, static_cast<size_t>(max_w) + max_h));
   ok(dev_alloc(&ctx->d_parent, N));
   ok(dev_alloc(&ctx->d_count, N));
-  ok(dev_alloc(&ctx->d_slot, N));
   ok(dev_alloc(&ctx->d_flags, N));
-  ok(dev_alloc(&ctx->d_speed, N));
+  ok(dev_alloc(&ctx->d_list, N));
   ok(dev_alloc(&ctx->d_member_speed, N));
   ok(dev_alloc(&ctx->d_member_pixel, N));
   ok(dev_alloc(&ctx->d_mask_own, N));
   ok(dev_alloc(&ctx->d_frame_ints, static_cast<size_t>(2) * max_batch));
-  ok(dev_alloc(&ctx->d_work, 2));
+  ok(dev_alloc(&ctx->d_work, 4));
   ok(dev_alloc(&ctx->d_stats, C));
   ok(dev_alloc(&ctx->d_work_items, C));
   ok(dev_alloc(&ctx->d_member_offset, C));
@@ -399,9 +402,8 @@ void mod_destroy(mod_ctx* ctx) {
   cudaFree(ctx->d_ray);
   cudaFree(ctx->d_parent);
   cudaFree(ctx->d_count);
-  cudaFree(ctx->d_slot);
   cudaFree(ctx->d_flags);
-  cudaFree(ctx->d_speed);
+  cudaFree(ctx->d_list);
   cudaFree(ctx->d_member_speed);
   cudaFree(ctx->d_member_pixel);
   cudaFree(ctx->d_mask_own);
@@ -523,7 +525,7 @@ int mod_scene_flow_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int bat
   if (!cam || !pairs || !params || !d_points32 || frame_stride_points < static_cast<size_t>(w) * h)
     return fail(ctx, MOD_ERR_INVALID_ARG, "null argument or frame stride smaller than a frame");
   MOD_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   return run_scene_flow_dev(ctx, s, w, h, batch, *cam, pairs, *params, dynamic_speed, static_cast<float*>(d_points32),
                             frame_stride_points, d_mask, d_opt_depth, d_opt_static_flow);
 }
@@ -536,7 +538,7 @@ int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch,
   if (!d_points32 || !params || frame_stride_points < static_cast<size_t>(w) * h)
     return fail(ctx, MOD_ERR_INVALID_ARG, "null argument or frame stride smaller than a frame");
   MOD_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   return run_cluster_dev(ctx, s, w, h, batch, static_cast<const float*>(d_points32), frame_stride_points, d_mask,
                          *params, d_opt_labels, d_objs, max_objs, d_stats);
 }

@@ -56,10 +56,8 @@ struct ClLaunch {
   int max_objs;
   // per-pixel workspaces, batch * w*h
   int* parent;
-  int* count;            // component size, valid at roots
-  int* slot;             // survivor slot, valid at roots (-1 = removed)
+  int* count;            // at roots: component size (cl_flatten), then survivor slot or -1 (cl_slots)
   uint8_t* flags;        // bit0: pixel has an accepted up-left neighbour
-  float* speed;          // |v| of survivor members
   // per-frame workspaces
   int* n_slots;          // [batch]
   int* n_dynamic;        // [batch]
@@ -77,8 +75,6 @@ struct ClusterStat {
   int rank;          // final cluster id (rank of key among the frame's survivors)
   uint32_t mn[3];    // order-preserving encodings of float min x,y,z
   uint32_t mx[3];
-  uint32_t sel_prefix;  // radix-select state: bits of the k-th largest speed decided so far
-  uint32_t sel_k;       // remaining rank inside the current prefix bucket (0-based, counted from the largest)
   int median_idx;       // pixel index whose speed equals the selected value (smallest index among ties)
   int pad;
 };
@@ -89,8 +85,9 @@ cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame
                                int h, int batch, float speed_thr);
 // Workspaces of the clusterer that are not indexed per pixel in ClLaunch.
 struct ClExtra {
-  int* work_count;         // [1]   (work_cursor must follow it directly)
-  int* work_cursor;        // [1]
+  int* work_count;         // [4]   work_count, work_cursor, list_count, border_count (adjacent: one reset)
+  int* work_cursor;        // = work_count + 1
+  uint32_t* list;          // [batch * w*h]  compacted global indices (frame*P + i) of the dynamic pixels
   int2* work_items;        // [batch * max_clusters]  (frame, slot) of every surviving cluster
   int* member_offset;      // [batch * max_clusters]  start of the cluster's member list inside its frame
   int* cursor;             // [batch * max_clusters]  fill level of the member list
