@@ -45,12 +45,13 @@ struct mod_ctx {
   // clusterer workspaces (max_batch frames)
   int* d_parent = nullptr;
   int* d_count = nullptr;
-  uint8_t* d_flags = nullptr;
+  TileStat* d_tstat = nullptr;
   uint32_t* d_list = nullptr;
+  uint32_t* d_border_mask = nullptr;
   uint32_t* d_member_speed = nullptr;
   int* d_member_pixel = nullptr;
   int* d_frame_ints = nullptr;  // n_slots[max_batch], n_dynamic[max_batch]
-  int* d_work = nullptr;        // work_count, work_cursor, list_count
+  int* d_work = nullptr;        // work_count, work_cursor, list_count, border_count, root_count
   ClusterStat* d_stats = nullptr;
   int2* d_work_items = nullptr;
   int* d_member_offset = nullptr;
@@ -240,7 +241,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   L.max_objs = max_objs;
   L.parent = ctx->d_parent;
   L.count = ctx->d_count;
-  L.flags = ctx->d_flags;
+  L.tstat = ctx->d_tstat;
   L.n_slots = ctx->d_frame_ints;
   L.n_dynamic = ctx->d_frame_ints + batch;  // adjacent: one reset kernel clears both
   L.stats = ctx->d_stats;
@@ -251,6 +252,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   X.work_count = ctx->d_work;
   X.work_cursor = ctx->d_work + 1;
   X.list = ctx->d_list;
+  X.border_mask = ctx->d_border_mask;
   X.work_items = ctx->d_work_items;
   X.member_offset = ctx->d_member_offset;
   X.cursor = ctx->d_cursor;
@@ -376,13 +378,14 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   ok(dev_alloc(&ctx->d_ray, static_cast<size_t>(max_w) + max_h));
   ok(dev_alloc(&ctx->d_parent, N));
   ok(dev_alloc(&ctx->d_count, N));
-  ok(dev_alloc(&ctx->d_flags, N));
+  ok(dev_alloc(&ctx->d_tstat, N));
   ok(dev_alloc(&ctx->d_list, N));
+  ok(dev_alloc(&ctx->d_border_mask, N));
   ok(dev_alloc(&ctx->d_member_speed, N));
   ok(dev_alloc(&ctx->d_member_pixel, N));
   ok(dev_alloc(&ctx->d_mask_own, N));
   ok(dev_alloc(&ctx->d_frame_ints, static_cast<size_t>(2) * max_batch));
-  ok(dev_alloc(&ctx->d_work, 4));
+  ok(dev_alloc(&ctx->d_work, 8));
   ok(dev_alloc(&ctx->d_stats, C));
   ok(dev_alloc(&ctx->d_work_items, C));
   ok(dev_alloc(&ctx->d_member_offset, C));
@@ -402,8 +405,9 @@ void mod_destroy(mod_ctx* ctx) {
   cudaFree(ctx->d_ray);
   cudaFree(ctx->d_parent);
   cudaFree(ctx->d_count);
-  cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_tstat);
   cudaFree(ctx->d_list);
+  cudaFree(ctx->d_border_mask);
   cudaFree(ctx->d_member_speed);
   cudaFree(ctx->d_member_pixel);
   cudaFree(ctx->d_mask_own);

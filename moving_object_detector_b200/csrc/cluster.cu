@@ -18,19 +18,20 @@
 //     among the surviving components.  cl_stats/cl_rank reproduce that, so ids (and the order of the
 //     MovingObjectArray) match the reference exactly, not only up to permutation.
 //
-// Pipeline (batched over frames).  The 1-byte dynamic mask is read ONCE (16 bytes per thread); everything after
-// works on the compacted list of dynamic pixels, so cost scales with the number of dynamic pixels:
-//   cl_tile      one CTA per 32x32 tile: mask+z tile with an N-pixel top/left halo staged in shared memory, tile-local
-//                union-find in shared memory over the edges that are not implied by a shorter accepted 2-path (see
-//                window_edges), then parent[i] = tile-local root, count[i] = 0, dynamic pixels appended to a list
-//   cl_merge     pixels within N of their tile's top/left border: the same window logic on global memory, lock-free
-//                union (atomicMin + path halving) of the edges that cross a tile border
-//   cl_flatten   parent[i] = root ; count[root] += 1 (warp-aggregated)
-//   cl_slots     roots with count >= cluster_size claim a dense survivor slot (stored over count[root])
-//   cl_stats     per-slot min/max of x,y,z and reference-order key: warp-shuffle reduction per cluster, then atomics
+// Pipeline (batched over frames); only cl_tile, cl_scatter (and the optional cl_labels) touch every dynamic pixel:
+//   cl_tile      one CTA per 32x32 tile.  Mask words + z of the tile and its N-pixel top/left halo are staged in shared
+//                memory; every dynamic pixel evaluates its window once (SIMD, see window_edges) and the surviving
+//                edges inside the tile are unioned in a shared-memory union-find.  The tile then publishes
+//                parent[pixel] = tile root, per-tile-root partial statistics (size, reference-order key, min/max of
+//                x,y,z; warp-shuffle reduced, then atomics), and three compact lists: dynamic pixels, pixels with an
+//                edge leaving the tile, tile roots.
+//   cl_merge     border list: the same window logic on global memory, lock-free union (atomicMin + path halving)
+//                of the edges that cross a tile border.  All union-find nodes touched here are tile roots.
+//   cl_roots     tile-root list: parent[r] = final root R; partial statistics of r are merged into R
+//   cl_slots     final roots with size >= cluster_size claim a dense survivor slot (removeSmallClusters)
 //   cl_rank      per frame: final ids by key rank, member-list offsets, work queue for cl_objects
 //   cl_scatter   survivors' members -> contiguous per-cluster lists (speed bits, pixel index)
-//   cl_objects   one CTA per cluster: 4-pass 8-bit radix select of the (n/2)-th largest |v|, emit MovingObject
+//   cl_objects   one CTA per cluster: 3-pass (11/11/10 bit) radix select of the (n/2)-th largest |v|, MovingObject
 //   cl_labels    optional dense label image (cluster_map_)
 
 #include <math_constants.h>
@@ -210,84 +211,229 @@ __device__ __forceinline__ void smem_union(int* lab, int a, int b) {
   }
 }
 
+// Appends `flag` lanes' `value` to a shared-memory list (order inside a warp preserved, warps unordered); returns the
+// position written (or -1).
+__device__ __forceinline__ int smem_append(bool flag, uint16_t value, uint16_t* list, int* counter) {
+  const unsigned ballot = __ballot_sync(kFull, flag);
+  if (ballot == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(counter, __popc(ballot));
+  base = __shfl_sync(kFull, base, 0);
+  const int pos = base + __popc(ballot & ((1u << lane) - 1));
+  if (flag) list[pos] = value;
+  return flag ? pos : -1;
+}
+
+// Flag bits of a staged pixel
+constexpr uint8_t kDyn = 1;   // dynamic
+constexpr uint8_t kLeft = 2;  // edge to the left neighbour accepted  (both dynamic, depth gate passes)
+constexpr uint8_t kUp = 4;    // edge to the upper neighbour accepted
+
+// NC in 1..4 selects the fast path: per-pixel left/up edge bits are computed once per tile, horizontal runs are
+// labelled without any union-find traffic, the "implied edge" tests become a handful of bit operations on 25-bit
+// window masks, and a vertical unit edge is dropped when the 4-cycle p, p-(1,0), up(p)-(1,0), up(p) is closed by
+// accepted unit edges (its endpoints are then connected through the up-edge one pixel to the left, by induction on x).
+// NC == 0 is the generic path for N in 5..10 (runtime N, window_edges).
 template <int NC>
 __global__ void __launch_bounds__(kBlock)
-    cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, int* __restrict__ list_count,
-                   uint32_t* __restrict__ border_list, int* __restrict__ border_count) {
+    cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ border_list,
+                   uint32_t* __restrict__ border_mask, uint32_t* __restrict__ root_list,
+                   int* __restrict__ counters /* list, border, root */) {
   constexpr int kMaxN = 10;
   constexpr int HN = NC > 0 ? NC : kMaxN;  // halo capacity
   constexpr int SW = kTileW + HN;          // shared-memory row pitch
+  constexpr bool kFast = NC > 0;
   const int N = NC > 0 ? NC : L.n;
   const int stride = N + 1;
-  __shared__ uint8_t s_m[(kTileH + HN) * SW];
+  __shared__ __align__(16) uint8_t s_m[(kTileH + HN) * SW];
   __shared__ float s_z[(kTileH + HN) * SW];
-  __shared__ int s_lab[kTileW * kTileH];
+  __shared__ __align__(16) int s_lab[kTileW * kTileH];
+  __shared__ uint8_t s_up[kTileW * kTileH];  // pixel has an accepted up-left neighbour
   __shared__ uint16_t s_dl[kTileW * kTileH];
   __shared__ uint16_t s_bl[kTileW * kTileH];
-  __shared__ int s_cnt, s_bcnt, s_base, s_bbase;
+  __shared__ uint32_t s_bx[kFast ? kTileW * kTileH : 1];
+  __shared__ uint16_t s_rl[kTileW * kTileH];
+  __shared__ int s_cnt, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase;
   const int frame = blockIdx.z;
   const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
   const size_t P = static_cast<size_t>(L.w) * L.h;
-  const uint8_t* mask = L.mask + frame * P;
+  const size_t fb = frame * P;
+  const uint8_t* mask = L.mask + fb;
   const float* pts = L.points + frame * L.points_frame_stride * 8;
   const int lane = threadIdx.x & 31;
 
-  // A: mask of the tile plus its N-pixel top/left halo; shared (sy,sx) <-> pixel (ty0-N+sy, tx0-N+sx)
-  if (threadIdx.x == 0) {
-    s_cnt = 0;
-    s_bcnt = 0;
-  }
-  const int span_w = kTileW + N, span_h = kTileH + N;
-  bool any_core = false;
-  for (int k = threadIdx.x; k < span_w * span_h; k += kBlock) {
-    const int sy = k / span_w, sx = k - sy * span_w;
-    const int y = ty0 - N + sy, x = tx0 - N + sx;
-    uint8_t m = 0;
-    if (x >= 0 && y >= 0 && x < L.w && y < L.h) m = mask[static_cast<size_t>(y) * L.w + x];
-    s_m[sy * SW + sx] = m;
-    any_core = any_core || (m != 0 && sy >= N && sx >= N);
-  }
-  if (!__syncthreads_or(any_core)) return;
+  if (threadIdx.x == 0) s_cnt = s_bcnt = s_rcnt = 0;
 
-  // B: z of the dynamic pixels (strided gather out of the 32-byte records), label init, tile-local dynamic list
-  for (int k = threadIdx.x; k < span_w * span_h; k += kBlock) {
-    const int sy = k / span_w, sx = k - sy * span_w;
-    if (s_m[sy * SW + sx])
-      s_z[sy * SW + sx] = __ldg(pts + (static_cast<size_t>(ty0 - N + sy) * L.w + (tx0 - N + sx)) * 8 + 2);
+  // A: the 32x32 core, one 4-pixel mask word per thread
+  const int row = threadIdx.x >> 3, wq = threadIdx.x & 7;
+  const int y = ty0 + row, x0 = tx0 + wq * 4;
+  uint32_t word = 0;
+  if (y < L.h && x0 < L.w) {
+    const uint8_t* src = mask + static_cast<size_t>(y) * L.w + x0;
+    if (x0 + 3 < L.w && (reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+      word = __ldg(reinterpret_cast<const uint32_t*>(src));
+    } else {
+      for (int j = 0; j < 4 && x0 + j < L.w; j++) word |= static_cast<uint32_t>(src[j]) << (8 * j);
+    }
   }
-  for (int c = threadIdx.x; c < kTileW * kTileH; c += kBlock) {  // a warp covers one tile row
-    const int ly = c >> 5, lx = c & 31;
-    const bool dyn = s_m[(ly + N) * SW + lx + N] != 0;
-    s_lab[c] = dyn ? c : -1;
-    const unsigned ballot = __ballot_sync(kFull, dyn);
-    int base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(&s_cnt, __popc(ballot));
-    base = __shfl_sync(kFull, base, 0);
-    if (dyn) s_dl[base + __popc(ballot & ((1u << lane) - 1))] = static_cast<uint16_t>(c);
+  if (!__syncthreads_or(word != 0)) return;  // no dynamic pixel in this tile
+
+  const int c0 = row * kTileW + wq * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const bool dyn = ((word >> (8 * j)) & 0xffu) != 0;
+    const int si = (row + N) * SW + N + wq * 4 + j;
+    s_m[si] = dyn ? kDyn : 0;
+    if (dyn) s_z[si] = __ldg(pts + (static_cast<size_t>(y) * L.w + x0 + j) * 8 + 2);
+  }
+  // halo: N rows above (full width 32+N) and N columns to the left of the core
+  const int top = N * (kTileW + N);
+  const int n_halo = top + kTileH * N;
+  for (int k = threadIdx.x; k < n_halo; k += kBlock) {
+    int sy, sx;
+    if (k < top) {
+      sy = k / (kTileW + N);
+      sx = k - sy * (kTileW + N);
+    } else {
+      const int k2 = k - top;
+      sy = N + k2 / N;
+      sx = k2 - (k2 / N) * N;
+    }
+    const int yy = ty0 - N + sy, xx = tx0 - N + sx;
+    uint8_t m = 0;
+    if (xx >= 0 && yy >= 0 && xx < L.w && yy < L.h) m = mask[static_cast<size_t>(yy) * L.w + xx] ? kDyn : 0;
+    s_m[sy * SW + sx] = m;
+    if (m) s_z[sy * SW + sx] = __ldg(pts + (static_cast<size_t>(yy) * L.w + xx) * 8 + 2);
+  }
+  __syncthreads();
+
+  if constexpr (kFast) {
+    // A2: left / up edge bits of every staged dynamic pixel whose neighbour is staged too
+    constexpr int span = kTileW + NC;
+    uint8_t add[(span * span + kBlock - 1) / kBlock];
+#pragma unroll
+    for (int it = 0; it < (span * span + kBlock - 1) / kBlock; it++) {
+      const int k = it * kBlock + threadIdx.x;
+      add[it] = 0;
+      if (k < span * span) {
+        const int sy = k / span, sx = k - sy * span;
+        const int si = sy * SW + sx;
+        if (s_m[si]) {
+          const float z = s_z[si];
+          if (sx > 0 && s_m[si - 1] && depth_gate(z, s_z[si - 1], L.depth_thr)) add[it] |= kLeft;
+          if (sy > 0 && s_m[si - SW] && depth_gate(z, s_z[si - SW], L.depth_thr)) add[it] |= kUp;
+        }
+      }
+    }
+    __syncthreads();  // all dynamic bits read before any flag byte changes
+#pragma unroll
+    for (int it = 0; it < (span * span + kBlock - 1) / kBlock; it++) {
+      const int k = it * kBlock + threadIdx.x;
+      if (k < span * span && add[it]) {
+        const int sy = k / span, sx = k - sy * span;
+        s_m[sy * SW + sx] |= add[it];
+      }
+    }
+    __syncthreads();
+  }
+
+  // B: initial labels and the tile-local list of dynamic pixels
+  {
+    uint8_t f[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) f[j] = s_m[(row + N) * SW + N + wq * 4 + j];
+    int lab4[4];
+    if constexpr (kFast) {
+      // horizontal runs: a pixel starts a run unless its left edge is accepted and the left pixel is in the core
+      uint32_t nib = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const bool starts = (f[j] & kDyn) && !((f[j] & kLeft) && (wq * 4 + j) > 0);
+        nib |= static_cast<uint32_t>(starts) << (wq * 4 + j);
+      }
+      // the 8 threads of a row are 8 consecutive lanes: OR-reduce their nibbles
+      nib |= __shfl_xor_sync(kFull, nib, 1);
+      nib |= __shfl_xor_sync(kFull, nib, 2);
+      nib |= __shfl_xor_sync(kFull, nib, 4);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int lx = wq * 4 + j;
+        const uint32_t below = nib & ((2u << lx) - 1u);
+        lab4[j] = (f[j] & kDyn) ? row * kTileW + (31 - __clz(below)) : -1;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) lab4[j] = (f[j] & kDyn) ? c0 + j : -1;
+    }
+    *reinterpret_cast<int4*>(&s_lab[c0]) = make_int4(lab4[0], lab4[1], lab4[2], lab4[3]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) smem_append((f[j] & kDyn) != 0, static_cast<uint16_t>(c0 + j), s_dl, &s_cnt);
   }
   __syncthreads();
   const int nd = s_cnt;
 
-  // C: edge sets (SIMD), then tile-local unions in shared memory; pixels with an edge leaving the tile are noted
+  // C: edge sets (SIMD), then tile-local unions in shared memory; edges leaving the tile go to cl_merge
   for (int e0 = 0; e0 < nd; e0 += kBlock) {
     const int e = e0 + threadIdx.x;
     EdgeSetFor<NC> edges;
     edges.clear();
     int c = 0, lx = 0, ly = 0;
+    uint32_t cross = 0;  // fast path: window cells of the edges that leave the tile
     bool crosses = false;
     if (e < nd) {
       c = s_dl[e];
       ly = c >> 5;
       lx = c & 31;
-      const float z_here = s_z[(ly + N) * SW + lx + N];
-      auto probe = [&](int wx, int wy, float& z) {
-        const int si = (ly + wy) * SW + lx + wx;
-        if (!s_m[si]) return false;
-        z = s_z[si];
-        return true;
-      };
-      const bool any = window_edges<NC>(N, z_here, L.depth_thr, probe, edges);
-      L.flags[frame * P + static_cast<size_t>(ty0 + ly) * L.w + tx0 + lx] = any ? 1 : 0;
+      const int sa = (ly + N) * SW + lx + N;
+      const float z_here = s_z[sa];
+      if constexpr (kFast) {
+        constexpr int S = NC + 1;
+        constexpr int kA = NC * S + NC, kL = kA - 1, kU = kA - S;
+        uint32_t acc = 0, lm = 0, um = 0;
+#pragma unroll
+        for (int wy = 0; wy < S; wy++) {
+#pragma unroll
+          for (int wx = 0; wx < S; wx++) {
+            if (wy == NC && wx == NC) continue;
+            const int k = wy * S + wx;
+            const int si = (ly + wy) * SW + lx + wx;
+            const uint32_t f = s_m[si];
+            lm |= ((f >> 1) & 1u) << k;
+            um |= ((f >> 2) & 1u) << k;
+            if ((f & kDyn) && depth_gate(z_here, s_z[si], L.depth_thr)) acc |= 1u << k;
+          }
+        }
+        s_up[c] = acc != 0;
+        // cells whose right neighbour is still inside the window (wx < N)
+        uint32_t col_ok = 0;
+#pragma unroll
+        for (int wy = 0; wy < S; wy++) col_ok |= ((1u << NC) - 1u) << (wy * S);
+        uint32_t E = acc & ~(((acc & lm) >> 1) & col_ok) & ~((acc & um) >> S);
+        // unit edges: left is realised by the run labels inside the tile; up obeys the 4-cycle rule
+        const uint32_t own = s_m[sa];
+        const bool skip_up = (own & kLeft) && ((um >> kL) & 1u) && ((lm >> kU) & 1u);
+        if (skip_up) E &= ~(1u << kU);
+        if (lx > 0) E &= ~(1u << kL);
+        // split into tile-local and cross-tile edges: a cell (wx,wy) leaves the tile iff lx-N+wx < 0 or ly-N+wy < 0
+        uint32_t inside = 0;
+#pragma unroll
+        for (int wy = 0; wy < S; wy++) {
+          if (ly - NC + wy < 0) continue;
+          const int first = max(NC - lx, 0);  // wx >= first stays inside
+          if (first < S) inside |= ((((1u << S) - 1u) >> first) << first) << (wy * S);
+        }
+        cross = E & ~inside;
+        edges.w[0] = E & inside;
+      } else {
+        auto probe = [&](int wx, int wy, float& z) {
+          const int si = (ly + wy) * SW + lx + wx;
+          if (!s_m[si]) return false;
+          z = s_z[si];
+          return true;
+        };
+        s_up[c] = window_edges<NC>(N, z_here, L.depth_thr, probe, edges) ? 1 : 0;
+      }
     }
     while (__any_sync(kFull, !edges.empty())) {  // warp-uniform loop: lanes stay converged between unions
       if (!edges.empty()) {
@@ -297,48 +443,118 @@ __global__ void __launch_bounds__(kBlock)
         if (nx >= 0 && ny >= 0)
           smem_union(s_lab, c, ny * kTileW + nx);
         else
-          crosses = true;  // the up-left endpoint lies in another tile: cl_merge
+          crosses = true;  // generic path: the up-left endpoint lies in another tile, cl_merge recomputes
       }
       __syncwarp();
     }
-    const unsigned ballot = __ballot_sync(kFull, crosses);
-    if (ballot) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_bcnt, __popc(ballot));
-      base = __shfl_sync(kFull, base, 0);
-      if (crosses) s_bl[base + __popc(ballot & ((1u << lane) - 1))] = static_cast<uint16_t>(c);
+    const int pos = smem_append(crosses || cross != 0, static_cast<uint16_t>(c), s_bl, &s_bcnt);
+    if constexpr (kFast) {
+      if (pos >= 0) s_bx[pos] = cross;
     }
   }
   __syncthreads();
 
-  // D: flatten inside the tile and publish: parent = tile-local root (as a frame raster index), list entries
-  const int nb = s_bcnt;
+  // D1: flatten the tile-local forest; roots initialise their partial record
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {
+    const int e = e0 + threadIdx.x;
+    bool is_root = false;
+    int c = 0;
+    if (e < nd) {
+      c = s_dl[e];
+      const int r = smem_find(s_lab, c);
+      s_lab[c] = r;
+      is_root = (r == c);
+      if (is_root) {
+        const size_t gi = fb + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31);
+        L.count[gi] = 0;
+        TileStat init;
+        init.key = 0x7fffffff;
+        init.mn[0] = init.mn[1] = init.mn[2] = 0xffffffffu;
+        init.mx[0] = init.mx[1] = init.mx[2] = 0u;
+        init.pad = 0;
+        L.tstat[gi] = init;
+      }
+    }
+    smem_append(is_root, static_cast<uint16_t>(c), s_rl, &s_rcnt);
+  }
+  __syncthreads();
+  const int nb = s_bcnt, nr = s_rcnt;
   if (threadIdx.x == 0) {
-    s_base = atomicAdd(list_count, nd);
-    s_bbase = nb ? atomicAdd(border_count, nb) : 0;
+    s_base = atomicAdd(counters + 0, nd);
+    s_bbase = nb ? atomicAdd(counters + 1, nb) : 0;
+    s_rbase = atomicAdd(counters + 2, nr);
     atomicAdd(L.n_dynamic + frame, nd);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nd; e += kBlock) {
-    const int c = s_dl[e];
-    const int r = smem_find(s_lab, c);
-    const size_t i = static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31);
-    L.parent[frame * P + i] = (ty0 + (r >> 5)) * L.w + tx0 + (r & 31);
-    L.count[frame * P + i] = 0;
-    list[s_base + e] = static_cast<uint32_t>(frame * P + i);
+
+  // D2: publish parent = tile root, list entries, and the per-root partial statistics (pcl::getMinMax3D operands,
+  // size, reference-order key), reduced per tile root inside each warp (redux.sync) before the atomics
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {
+    const int e = e0 + threadIdx.x;
+    int r = -1 - lane;  // distinct for idle lanes
+    uint32_t ex_mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, ex_mx[3] = {0u, 0u, 0u};
+    int key = 0x7fffffff;
+    if (e < nd) {
+      const int c = s_dl[e];
+      r = s_lab[c];
+      const int i = (ty0 + (c >> 5)) * L.w + tx0 + (c & 31);
+      L.parent[fb + i] = (ty0 + (r >> 5)) * L.w + tx0 + (r & 31);
+      list[s_base + e] = static_cast<uint32_t>(fb + i);
+      const float4 xyz = __ldg(reinterpret_cast<const float4*>(pts + static_cast<size_t>(i) * 8));
+      const float cc[3] = {xyz.x, xyz.y, xyz.z};
+#pragma unroll
+      for (int k = 0; k < 3; k++)  // NaN coordinates are skipped (order dependent in the reference; unpinned)
+        if (!isnan(cc[k])) ex_mn[k] = ex_mx[k] = float_to_ordered(cc[k]);
+      if (s_up[c]) key = i;
+    }
+    unsigned todo = __ballot_sync(kFull, r >= 0);
+    while (todo) {  // peel one tile root at a time; usually one or two per warp
+      const int leader = __ffs(todo) - 1;
+      const int lr = __shfl_sync(kFull, r, leader);
+      const bool in = (r == lr);
+      const unsigned grp = __ballot_sync(kFull, in);
+      if (in) {
+        uint32_t mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          mn[k] = __reduce_min_sync(grp, ex_mn[k]);
+          mx[k] = __reduce_max_sync(grp, ex_mx[k]);
+        }
+        const int kk = __reduce_min_sync(grp, key);
+        if (lane == leader) {
+          const size_t gr = fb + static_cast<size_t>(ty0 + (lr >> 5)) * L.w + tx0 + (lr & 31);
+          atomicAdd(L.count + gr, __popc(grp));
+          TileStat& st = L.tstat[gr];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            if (mn[k] != 0xffffffffu) atomicMin(&st.mn[k], mn[k]);
+            if (mx[k] != 0u) atomicMax(&st.mx[k], mx[k]);
+          }
+          if (kk != 0x7fffffff) atomicMin(&st.key, kk);
+        }
+      }
+      todo &= ~grp;
+    }
   }
   for (int e = threadIdx.x; e < nb; e += kBlock) {
     const int c = s_bl[e];
-    border_list[s_bbase + e] = static_cast<uint32_t>(frame * P + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31));
+    border_list[s_bbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31));
+    if constexpr (kFast) border_mask[s_bbase + e] = s_bx[e];
+  }
+  for (int e = threadIdx.x; e < nr; e += kBlock) {
+    const int c = s_rl[e];
+    root_list[s_rbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31));
   }
 }
 
 // ---- cl_merge -----------------------------------------------------------------------------------------------------
-// Edges whose up-left endpoint lies in another tile, for the pixels cl_tile put on the border list.  Same window logic,
-// on global memory; lock-free union with atomicMin + path halving.
+// Edges whose up-left endpoint lies in another tile, for the pixels cl_tile put on the border list; lock-free union
+// with atomicMin + path halving.  Fast path: cl_tile already decided which window cells to union (border_mask).
+// Generic path: the window logic is re-evaluated on global memory.
 template <int NC>
 __global__ void __launch_bounds__(kBlock)
-    cl_merge_kernel(const ClLaunch L, const uint32_t* __restrict__ border_list, const int* __restrict__ border_count) {
+    cl_merge_kernel(const ClLaunch L, const uint32_t* __restrict__ border_list,
+                    const uint32_t* __restrict__ border_mask, const int* __restrict__ border_count) {
   const int n = *border_count;
   const int N = NC > 0 ? NC : L.n;
   const int stride = N + 1;
@@ -355,19 +571,23 @@ __global__ void __launch_bounds__(kBlock)
       i = static_cast<int>(g - frame * P);
       v = i / L.w;
       u = i - v * L.w;
-      const uint8_t* mask = L.mask + static_cast<size_t>(frame) * P;
-      const float* pts = L.points + static_cast<size_t>(frame) * L.points_frame_stride * 8;
       parent = L.parent + static_cast<size_t>(frame) * P;
-      const float z_here = __ldg(pts + static_cast<size_t>(i) * 8 + 2);
-      auto probe = [&](int wx, int wy, float& z) {
-        const int uu = u - N + wx, vv = v - N + wy;
-        if (uu < 0 || vv < 0) return false;  // isInRange (uu <= u < w and vv <= v < h always hold)
-        const int j = vv * L.w + uu;
-        if (mask[j] == 0) return false;
-        z = __ldg(pts + static_cast<size_t>(j) * 8 + 2);
-        return true;
-      };
-      window_edges<NC>(N, z_here, L.depth_thr, probe, edges);
+      if constexpr (NC > 0) {
+        edges.w[0] = border_mask[t];
+      } else {
+        const uint8_t* mask = L.mask + static_cast<size_t>(frame) * P;
+        const float* pts = L.points + static_cast<size_t>(frame) * L.points_frame_stride * 8;
+        const float z_here = __ldg(pts + static_cast<size_t>(i) * 8 + 2);
+        auto probe = [&](int wx, int wy, float& z) {
+          const int uu = u - N + wx, vv = v - N + wy;
+          if (uu < 0 || vv < 0) return false;  // isInRange (uu <= u < w and vv <= v < h always hold)
+          const int j = vv * L.w + uu;
+          if (mask[j] == 0) return false;
+          z = __ldg(pts + static_cast<size_t>(j) * 8 + 2);
+          return true;
+        };
+        window_edges<NC>(N, z_here, L.depth_thr, probe, edges);
+      }
     }
     const int lx = u & (kTileW - 1), ly = v & (kTileH - 1);
     while (__any_sync(kFull, !edges.empty())) {
@@ -375,145 +595,80 @@ __global__ void __launch_bounds__(kBlock)
         const int k = edges.pop();
         const int wy = k / stride, wx = k - wy * stride;
         const int dx = wx - N, dy = wy - N;
-        if (lx + dx < 0 || ly + dy < 0) uf_union(parent, i, (v + dy) * L.w + (u + dx));  // other tile
+        if (NC > 0 || lx + dx < 0 || ly + dy < 0) uf_union(parent, i, (v + dy) * L.w + (u + dx));  // other tile
       }
       __syncwarp();
     }
   }
 }
 
-// ---- cl_flatten -------------------------------------------------------------------------------------------------
-// integrateConnectedClusters (:253-267) + the histogram of removeSmallClusters (:359-367)
+// ---- cl_roots -----------------------------------------------------------------------------------------------------
+// integrateConnectedClusters (:253-267) on the tile roots: parent[r] = final root R, and r's partial record is merged
+// into R's.  After this kernel every dynamic pixel reaches its final root in two hops (pixel -> tile root -> R).
 __global__ void __launch_bounds__(kBlock)
-    cl_flatten_kernel(const ClLaunch L, const uint32_t* __restrict__ list, const int* __restrict__ list_count) {
-  const int n = *list_count;
+    cl_roots_kernel(const ClLaunch L, const uint32_t* __restrict__ root_list, const int* __restrict__ root_count) {
+  const int n = *root_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
-  const int lane = threadIdx.x & 31;
   for (int t0 = blockIdx.x * kBlock; t0 < n; t0 += gridDim.x * kBlock) {
     const int t = t0 + threadIdx.x;
-    const bool active = t < n;
-    const unsigned ballot = __ballot_sync(kFull, active);
-    if (!active) continue;
-    const uint32_t g = list[t];
-    const uint32_t frame = g / P;
-    int* parent = L.parent + static_cast<size_t>(frame) * P;
-    const int root = uf_find(parent, static_cast<int>(g - frame * P));
-    L.parent[g] = root;
-    // warp-aggregated size count: lanes with the same root cell elect one leader
-    const uint32_t cell = frame * P + static_cast<uint32_t>(root);
-    const unsigned same = __match_any_sync(ballot, cell);
-    if (lane == __ffs(same) - 1) atomicAdd(L.count + cell, __popc(same));
+    if (t < n) {
+      const uint32_t g = root_list[t];
+      const uint32_t frame = g / P;
+      const int r = static_cast<int>(g - frame * P);
+      int* parent = L.parent + static_cast<size_t>(frame) * P;
+      const int R = uf_find(parent, r);
+      if (R != r) {
+        parent[r] = R;
+        const size_t gR = static_cast<size_t>(frame) * P + R;
+        const TileStat src = L.tstat[g];
+        TileStat& dst = L.tstat[gR];
+        atomicAdd(L.count + gR, L.count[g]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          if (src.mn[k] != 0xffffffffu) atomicMin(&dst.mn[k], src.mn[k]);
+          if (src.mx[k] != 0u) atomicMax(&dst.mx[k], src.mx[k]);
+        }
+        if (src.key != 0x7fffffff) atomicMin(&dst.key, src.key);
+      }
+    }
+    __syncwarp();
   }
 }
 
-// ---- cl_slots ---------------------------------------------------------------------------------------------------
+// ---- cl_slots -----------------------------------------------------------------------------------------------------
 // removeSmallClusters (:369-383): components below cluster_size are dropped; survivors get a dense slot, which is
-// stored over count[root] (the size moves into the slot's ClusterStat).
+// stored over count[R] (the size moves into the slot's ClusterStat together with the merged statistics).
 __global__ void __launch_bounds__(kBlock)
-    cl_slots_kernel(const ClLaunch L, const uint32_t* __restrict__ list, const int* __restrict__ list_count) {
-  const int n = *list_count;
+    cl_slots_kernel(const ClLaunch L, const uint32_t* __restrict__ root_list, const int* __restrict__ root_count) {
+  const int n = *root_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   for (int t = blockIdx.x * kBlock + threadIdx.x; t < n; t += gridDim.x * kBlock) {
-    const uint32_t g = list[t];
+    const uint32_t g = root_list[t];
     const uint32_t frame = g / P;
-    const int i = static_cast<int>(g - frame * P);
-    if (L.parent[g] != i) continue;  // not a root
+    const int r = static_cast<int>(g - frame * P);
+    if (L.parent[g] != r) continue;  // merged into another tile's root
     const int cnt = L.count[g];
     int s = -1;
     if (cnt >= L.min_size) {
       s = atomicAdd(L.n_slots + frame, 1);
       if (s < L.max_clusters) {
+        const TileStat ts = L.tstat[g];
         ClusterStat& st = L.stats[static_cast<size_t>(frame) * L.max_clusters + s];
-        st.root = i;
+        st.root = r;
         st.count = cnt;
-        st.key = 0x7fffffff;
+        st.key = ts.key;
         st.rank = -1;
-        st.mn[0] = st.mn[1] = st.mn[2] = 0xffffffffu;
-        st.mx[0] = st.mx[1] = st.mx[2] = 0u;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          st.mn[k] = ts.mn[k];
+          st.mx[k] = ts.mx[k];
+        }
         st.median_idx = 0x7fffffff;
       } else {
         s = -1;  // overflow: reported through frame_stats.status by cl_rank
       }
     }
     L.count[g] = s;
-  }
-}
-
-// ---- cl_stats ---------------------------------------------------------------------------------------------------
-// pcl::getMinMax3D over the members (cluster2MovingObject :151-152) and the reference-order key, reduced with warp
-// shuffles per cluster before touching the per-cluster atomics.
-__global__ void __launch_bounds__(kBlock)
-    cl_stats_kernel(const ClLaunch L, const uint32_t* __restrict__ list, const int* __restrict__ list_count) {
-  const int n = *list_count;
-  const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
-  const int lane = threadIdx.x & 31;
-  for (int t0 = blockIdx.x * kBlock; t0 < n; t0 += gridDim.x * kBlock) {
-    const int t = t0 + threadIdx.x;
-    int s = -1;
-    uint32_t frame = 0;
-    int i = 0;
-    uint32_t g = 0;
-    if (t < n) {
-      g = list[t];
-      frame = g / P;
-      i = static_cast<int>(g - frame * P);
-      s = L.count[frame * P + static_cast<uint32_t>(L.parent[g])];  // slot of the root (cl_slots)
-    }
-    const unsigned member = __ballot_sync(kFull, s >= 0);
-    if (member == 0) continue;
-    uint32_t ex_mn[3], ex_mx[3];
-    int key = 0x7fffffff;
-    long long group = -1 - lane;  // distinct for non-members so they never match each other
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      ex_mn[k] = 0xffffffffu;
-      ex_mx[k] = 0u;
-    }
-    if (s >= 0) {
-      const float* rec = L.points + (static_cast<size_t>(frame) * L.points_frame_stride + i) * 8;
-      const float4 xyz = __ldg(reinterpret_cast<const float4*>(rec));
-      const float c[3] = {xyz.x, xyz.y, xyz.z};
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        // NaN coordinates are skipped (the reference's running min/max is order dependent there; unpinned)
-        if (!isnan(c[k])) ex_mn[k] = ex_mx[k] = float_to_ordered(c[k]);
-      }
-      if (L.flags[g] & 1) key = i;
-      group = (static_cast<long long>(frame) << 32) | static_cast<unsigned>(s);
-    }
-    // Peel groups one at a time: usually one or two clusters per warp.
-    unsigned todo = member;
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const long long lg = __shfl_sync(kFull, group, leader);
-      const bool in = (group == lg);
-      uint32_t mn[3], mx[3];
-      int kk = in ? key : 0x7fffffff;
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        mn[k] = in ? ex_mn[k] : 0xffffffffu;
-        mx[k] = in ? ex_mx[k] : 0u;
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          mn[k] = min(mn[k], __shfl_xor_sync(kFull, mn[k], off));
-          mx[k] = max(mx[k], __shfl_xor_sync(kFull, mx[k], off));
-        }
-        kk = min(kk, __shfl_xor_sync(kFull, kk, off));
-      }
-      if (lane == leader) {
-        ClusterStat& st = L.stats[static_cast<size_t>(frame) * L.max_clusters + s];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          atomicMin(&st.mn[k], mn[k]);
-          atomicMax(&st.mx[k], mx[k]);
-        }
-        if (kk != 0x7fffffff) atomicMin(&st.key, kk);
-      }
-      todo &= ~__ballot_sync(kFull, in);
-    }
   }
 }
 
@@ -590,7 +745,8 @@ __global__ void __launch_bounds__(kBlock)
       const uint32_t g = list[t];
       frame = g / P;
       i = static_cast<int>(g - frame * P);
-      s = L.count[frame * P + static_cast<uint32_t>(L.parent[g])];
+      const uint32_t fbase = frame * P;
+      s = L.count[fbase + static_cast<uint32_t>(L.parent[fbase + static_cast<uint32_t>(L.parent[g])])];
     }
     const unsigned member = __ballot_sync(kFull, s >= 0);
     if (member == 0) continue;
@@ -616,26 +772,29 @@ __global__ void __launch_bounds__(kBlock)
 // ---- cl_objects -------------------------------------------------------------------------------------------------
 // cluster2MovingObject (:147-184) for one cluster per CTA (persistent CTAs pull clusters from the work queue):
 // bbox = max - min, centre = (min + max) / 2 (float), velocity = member with the (n/2)-th largest |v|.
-// The k-th largest is found by a 4-pass MSB-first radix select over the cluster's member list with a 256-bin
-// shared-memory histogram (warp-aggregated increments); lists up to kSmemMembers are staged in shared memory once.
+// The k-th largest is found by a 3-pass MSB-first radix select (11/11/10 bits) over the cluster's member list with a
+// 2048-bin shared-memory histogram (warp-aggregated increments) and a parallel suffix scan; lists up to kSmemMembers
+// are staged in shared memory once, longer ones stream from global memory with four loads in flight per thread.
 // Among members tied at the selected speed the smallest raster index is taken (the reference's std::sort leaves
 // ties unspecified).
-constexpr int kObjBlock = 512;
-constexpr int kSmemMembers = 10240;  // 40 KB
+constexpr int kObjBlock = 1024;
+constexpr int kSmemMembers = 9216;  // 36 KB
+constexpr int kBins = 2048;
 
 __global__ void __launch_bounds__(kObjBlock)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
                       int* __restrict__ work_cursor, const int* __restrict__ member_offset,
                       const uint32_t* __restrict__ member_speed, const int* __restrict__ member_pixel) {
   __shared__ uint32_t s_speed[kSmemMembers];
-  __shared__ unsigned hist[256];
+  __shared__ unsigned hist[kBins];
+  __shared__ unsigned s_wsum[kObjBlock / 32];
   __shared__ int s_item;
   __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_k;
   __shared__ int s_best;
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const int n_work = *work_count;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(work_cursor, 1);
     __syncthreads();
@@ -657,34 +816,66 @@ __global__ void __launch_bounds__(kObjBlock)
       s_k = static_cast<uint32_t>(n / 2);  // cluster.at(cluster.size() / 2) after the descending sort
       s_best = 0x7fffffff;
     }
-    for (int pass = 0; pass < 4; pass++) {
-      const int shift = 24 - 8 * pass;
-      if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    int decided = 0;  // number of high bits already fixed
+    for (int pass = 0; pass < 3; pass++) {
+      const int bits = pass < 2 ? 11 : 10;
+      const int shift = 32 - decided - bits;
+      for (int b = threadIdx.x; b < kBins; b += kObjBlock) hist[b] = 0;
       __syncthreads();
       const uint32_t prefix = s_prefix;
-      const uint32_t himask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
-      for (int j0 = 0; j0 < n; j0 += kObjBlock) {
-        const int j = j0 + threadIdx.x;
-        int bin = -1;
-        if (j < n) {
-          const uint32_t b = speeds[j];
-          if ((b & himask) == prefix) bin = static_cast<int>((b >> shift) & 0xff);
+      const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
+      const uint32_t binmask = (1u << bits) - 1u;
+      for (int j0 = 0; j0 < n; j0 += 4 * kObjBlock) {
+        uint32_t v[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int j = j0 + q * kObjBlock + threadIdx.x;
+          ok[q] = j < n;
+          v[q] = ok[q] ? speeds[j] : 0u;
         }
-        const unsigned same = __match_any_sync(kFull, bin);
-        if (bin >= 0 && lane == __ffs(same) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(same)));
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int bin = -1;
+          if (ok[q] && (v[q] & himask) == prefix) bin = static_cast<int>((v[q] >> shift) & binmask);
+          const unsigned same = __match_any_sync(kFull, bin);
+          if (bin >= 0 && lane == __ffs(same) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(same)));
+        }
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t k = s_k;
-        int bin = 255;
-        for (; bin > 0; bin--) {  // descending: k counts from the largest
-          const uint32_t c = hist[bin];
-          if (k < c) break;
-          k -= c;
-        }
-        s_k = k;
-        s_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
+      // parallel suffix scan: thread t owns bins hi = kBins-1-2t and hi-1 (descending order, k counts from the top)
+      const int hi = kBins - 1 - 2 * static_cast<int>(threadIdx.x);
+      const unsigned h0 = hist[hi], h1 = hist[hi - 1];
+      unsigned incl = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
       }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned ws = s_wsum[lane];
+        unsigned wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(kFull, wi, o);
+          if (lane >= o) wi += t;
+        }
+        s_wsum[lane] = wi - ws;  // exclusive
+      }
+      __syncthreads();
+      const unsigned before = s_wsum[warp] + incl - (h0 + h1);  // members in bins above `hi`
+      const uint32_t k = s_k;
+      __syncthreads();  // every thread has read s_k before it is overwritten
+      if (k >= before && k < before + h0) {
+        s_k = k - before;
+        s_prefix = prefix | (static_cast<uint32_t>(hi) << shift);
+      } else if (k >= before + h0 && k < before + h0 + h1) {
+        s_k = k - before - h0;
+        s_prefix = prefix | (static_cast<uint32_t>(hi - 1) << shift);
+      }
+      decided += bits;
       __syncthreads();
     }
     const uint32_t target = s_prefix;
@@ -728,7 +919,8 @@ __global__ void __launch_bounds__(kBlock) cl_labels_kernel(const ClLaunch L) {
     int label = -1;
     if (L.mask[g] != 0) {
       const size_t frame = g / P;
-      const int s = L.count[frame * P + L.parent[g]];
+      const size_t fb = frame * P;
+      const int s = L.count[fb + L.parent[fb + L.parent[g]]];  // pixel -> tile root -> final root -> slot
       if (s >= 0) label = L.stats[frame * L.max_clusters + s].rank;
     }
     L.labels[g] = label;
@@ -742,6 +934,14 @@ __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, si
   if (t < nc) c[t] = 0;
 }
 
+template <int NC>
+void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint32_t* border_list, uint32_t* root_list,
+                       int* counters) {
+  const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
+  cl_tile_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, border_list, X.border_mask, root_list, counters);
+  cl_merge_kernel<NC><<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
+}
+
 }  // namespace
 
 cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, int* n_launches) {
@@ -750,45 +950,37 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
   const size_t n_fs = static_cast<size_t>(L.batch);
   const size_t n_cs = static_cast<size_t>(L.batch) * L.max_clusters;
   {
-    // zero n_slots / n_dynamic (adjacent, 2*batch), cursor (batch*max_clusters), and the four counters
-    // work_count, work_cursor, list_count, border_count
+    // zero n_slots / n_dynamic (adjacent, 2*batch), cursor (batch*max_clusters), and the five counters
+    // work_count, work_cursor, list_count, border_count, root_count
     const size_t m = n_cs > 2 * n_fs ? n_cs : 2 * n_fs;
     cl_reset_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(L.n_slots, 2 * n_fs, X.cursor, n_cs,
-                                                                          X.work_count, 4);
+                                                                          X.work_count, 5);
   }
-  int* list_count = X.work_count + 2;
-  int* border_count = X.work_count + 3;
-  uint32_t* border_list = reinterpret_cast<uint32_t*>(X.member_pixel);  // free until cl_scatter
-  const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
+  int* counters = X.work_count + 2;  // list_count, border_count, root_count
+  // both lists are consumed before cl_scatter fills the member arrays they borrow
+  uint32_t* border_list = reinterpret_cast<uint32_t*>(X.member_pixel);
+  uint32_t* root_list = X.member_speed;
   switch (L.n) {
-    case 1: cl_tile_kernel<1><<<tgrid, kBlock, 0, s>>>(L, X.list, list_count, border_list, border_count); break;
-    case 2: cl_tile_kernel<2><<<tgrid, kBlock, 0, s>>>(L, X.list, list_count, border_list, border_count); break;
-    case 3: cl_tile_kernel<3><<<tgrid, kBlock, 0, s>>>(L, X.list, list_count, border_list, border_count); break;
-    case 4: cl_tile_kernel<4><<<tgrid, kBlock, 0, s>>>(L, X.list, list_count, border_list, border_count); break;
-    default: cl_tile_kernel<0><<<tgrid, kBlock, 0, s>>>(L, X.list, list_count, border_list, border_count); break;
+    case 1: launch_tile_merge<1>(s, L, X, border_list, root_list, counters); break;
+    case 2: launch_tile_merge<2>(s, L, X, border_list, root_list, counters); break;
+    case 3: launch_tile_merge<3>(s, L, X, border_list, root_list, counters); break;
+    case 4: launch_tile_merge<4>(s, L, X, border_list, root_list, counters); break;
+    default: launch_tile_merge<0>(s, L, X, border_list, root_list, counters); break;
   }
-  switch (L.n) {
-    case 1: cl_merge_kernel<1><<<kListGrid, kBlock, 0, s>>>(L, border_list, border_count); break;
-    case 2: cl_merge_kernel<2><<<kListGrid, kBlock, 0, s>>>(L, border_list, border_count); break;
-    case 3: cl_merge_kernel<3><<<kListGrid, kBlock, 0, s>>>(L, border_list, border_count); break;
-    case 4: cl_merge_kernel<4><<<kListGrid, kBlock, 0, s>>>(L, border_list, border_count); break;
-    default: cl_merge_kernel<0><<<kListGrid, kBlock, 0, s>>>(L, border_list, border_count); break;
-  }
-  cl_flatten_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, list_count);
-  cl_slots_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, list_count);
-  cl_stats_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, list_count);
+  cl_roots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
+  cl_slots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
   cl_rank_kernel<<<L.batch, kBlock, static_cast<size_t>(L.max_clusters) * sizeof(int), s>>>(L, X.work_count, X.work_items,
                                                                                           X.member_offset);
-  cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, list_count, X.member_offset, X.cursor, X.member_speed,
+  cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, counters, X.member_offset, X.cursor, X.member_speed,
                                                  X.member_pixel);
-  cl_objects_kernel<<<148 * 2, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
-                                                  X.member_speed, X.member_pixel);
+  cl_objects_kernel<<<148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
+                                              X.member_speed, X.member_pixel);
   if (L.labels != nullptr) {
     size_t lb = (total + kBlock - 1) / kBlock;
     if (lb > 148 * 16) lb = 148 * 16;
     cl_labels_kernel<<<static_cast<unsigned>(lb), kBlock, 0, s>>>(L);
   }
-  if (n_launches) *n_launches = 9 + (L.labels != nullptr ? 1 : 0);
+  if (n_launches) *n_launches = 8 + (L.labels != nullptr ? 1 : 0);
   return cudaGetLastError();
 }
 

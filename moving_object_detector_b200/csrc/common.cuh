@@ -56,8 +56,9 @@ struct ClLaunch {
   int max_objs;
   // per-pixel workspaces, batch * w*h
   int* parent;
-  int* count;            // at roots: component size (cl_flatten), then survivor slot or -1 (cl_slots)
-  uint8_t* flags;        // bit0: pixel has an accepted up-left neighbour
+  int* count;            // at tile roots: component size (cl_tile, merged by cl_roots); at final roots after
+                         // cl_slots: survivor slot or -1
+  struct TileStat* tstat;  // at tile roots: partial statistics (cl_tile), merged into the final root by cl_roots
   // per-frame workspaces
   int* n_slots;          // [batch]
   int* n_dynamic;        // [batch]
@@ -66,6 +67,13 @@ struct ClLaunch {
   int32_t* labels;       // may be null
   mod_object* objs;
   mod_frame_stats* frame_stats;
+};
+
+struct __align__(32) TileStat {
+  int key;           // min raster index of a member with an accepted up-left neighbour
+  uint32_t mn[3];    // order-preserving encodings of float min x,y,z
+  uint32_t mx[3];
+  int pad;
 };
 
 struct ClusterStat {
@@ -85,9 +93,10 @@ cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame
                                int h, int batch, float speed_thr);
 // Workspaces of the clusterer that are not indexed per pixel in ClLaunch.
 struct ClExtra {
-  int* work_count;         // [4]   work_count, work_cursor, list_count, border_count (adjacent: one reset)
+  int* work_count;         // [5]   work_count, work_cursor, list_count, border_count, root_count (one reset)
   int* work_cursor;        // = work_count + 1
   uint32_t* list;          // [batch * w*h]  compacted global indices (frame*P + i) of the dynamic pixels
+  uint32_t* border_mask;   // [batch * w*h]  per border-list entry: window cells of its cross-tile edges (N <= 4)
   int2* work_items;        // [batch * max_clusters]  (frame, slot) of every surviving cluster
   int* member_offset;      // [batch * max_clusters]  start of the cluster's member list inside its frame
   int* cursor;             // [batch * max_clusters]  fill level of the member list
