@@ -123,6 +123,11 @@ unsigned long long mod_launch_count(const mod_ctx* ctx);
 /* The context's own non-blocking stream (a cudaStream_t), usable as the `stream` argument of the *_dev calls. */
 void* mod_stream(const mod_ctx* ctx);
 
+/* Numerics self-check used by the tests: counts, into *d_n_bad, the operand pairs (d_a[i], d_b[i]) for which the kernel's
+ * FP64-pipe float division differs bitwise from IEEE float division (__fdiv_rn, i.e. the reference's divss). */
+int mod_selfcheck_fdiv(mod_ctx* ctx, void* stream, const float* d_a, const float* d_b, size_t n,
+                       unsigned long long* d_n_bad);
+
 /* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
 void* mod_host_alloc(size_t bytes);
 void mod_host_free(void* p);

@@ -345,6 +345,15 @@ const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null c
 
 unsigned long long mod_launch_count(const mod_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mod_selfcheck_fdiv(mod_ctx* ctx, void* stream, const float* d_a, const float* d_b, size_t n,
+                       unsigned long long* d_n_bad) {
+  if (!ctx || !d_a || !d_b || !d_n_bad) return MOD_ERR_INVALID_ARG;
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  MOD_CK(ctx, launch_fdiv_check(static_cast<cudaStream_t>(stream), d_a, d_b, n, d_n_bad));
+  ctx->launches++;
+  return MOD_OK;
+}
+
 void* mod_stream(const mod_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {

@@ -89,6 +89,7 @@ struct ClusterStat {
 
 void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, int w, int h, const mod_camera& cam);
 cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs);
+cudaError_t launch_fdiv_check(cudaStream_t s, const float* a, const float* b, size_t n, unsigned long long* n_bad);
 cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame_stride_points, uint8_t* mask, int w,
                                int h, int batch, float speed_thr);
 // Workspaces of the clusterer that are not indexed per pixel in ClLaunch.
