@@ -128,6 +128,19 @@ void* mod_stream(const mod_ctx* ctx);
 int mod_selfcheck_fdiv(mod_ctx* ctx, void* stream, const float* d_a, const float* d_b, size_t n,
                        unsigned long long* d_n_bad);
 
+/* ---- O(1) host-side parameter preparation, exposed so the CPU test-suite can pin it without a GPU ---------- */
+/* tf2::transformToEigen + Eigen::Quaterniond::toRotationMatrix (scene_flow_constructor.cpp:411; no normalisation):
+ * row-major R9 and translation t3, in the order of operations of Eigen 3.3. */
+void mod_host_rotation(const mod_transform* t, double* R9, double* t3);
+/* float equivalents of the reference's float-vs-double comparisons (clusterer_nodelet.cpp:51,176,198):
+ * (double)a >= th  <=>  a >= mod_host_threshold_ge(th);   (double)a > th  <=>  a > mod_host_threshold_gt(th). */
+float mod_host_threshold_ge(double th);
+float mod_host_threshold_gt(double th);
+/* sqrt-free form of "std::sqrt(s) >= thr" for a float sum of squares s >= +0 (scene_flow_constructor.cpp:198,
+ * clusterer_nodelet.cpp:51): the smallest float s2 with sqrtf(s2) >= thr, so that sqrtf(s) >= thr <=> s >= s2
+ * (sqrtf is correctly rounded and monotonic; NaN compares false on both sides). */
+float mod_host_sq_threshold(float thr);
+
 /* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
 void* mod_host_alloc(size_t bytes);
 void mod_host_free(void* p);

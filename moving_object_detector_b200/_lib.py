@@ -87,6 +87,10 @@ PROTOTYPES = {
     "mod_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mod_stream": (C.c_void_p, [C.c_void_p]),
     "mod_selfcheck_fdiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mod_host_rotation": (None, [C.POINTER(Transform), C.c_void_p, C.c_void_p]),
+    "mod_host_threshold_ge": (C.c_float, [C.c_double]),
+    "mod_host_threshold_gt": (C.c_float, [C.c_double]),
+    "mod_host_sq_threshold": (C.c_float, [C.c_float]),
     "mod_host_alloc": (C.c_void_p, [C.c_size_t]),
     "mod_host_free": (None, [C.c_void_p]),
     "mod_scene_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(Disparity),

@@ -24,6 +24,18 @@ float float_floor_of_double(double th) {
   return f;
 }
 
+// smallest float s2 >= +0 with sqrtf(s2) >= thr (sqrtf: IEEE correctly rounded on the host and as __fsqrt_rn)
+float sq_threshold(float thr) {
+  if (std::isnan(thr)) return thr;          // comparisons with NaN are false on both sides
+  if (!(thr > 0.0f)) return 0.0f;           // every s >= +0 passes
+  if (std::isinf(thr)) return thr;          // only s = +inf passes
+  float s = thr * thr;                      // within a few ulps of the boundary
+  if (std::isinf(s)) s = 3.402823466e38f;
+  while (s > 0.0f && sqrtf(nextafterf(s, 0.0f)) >= thr) s = nextafterf(s, 0.0f);
+  while (sqrtf(s) < thr) s = nextafterf(s, INFINITY);
+  return s;
+}
+
 }  // namespace mod
 
 using namespace mod;
@@ -331,6 +343,17 @@ int fetch_objects(mod_ctx* ctx, cudaStream_t s, mod_object* objs, int32_t max_ob
 extern "C" {
 
 int mod_abi_version(void) { return MOD_B200_ABI_VERSION; }
+
+void mod_host_rotation(const mod_transform* t, double* R9, double* t3) {
+  if (!t) return;
+  SfPair p;
+  fill_transform(*t, p);
+  if (R9) std::memcpy(R9, p.R, sizeof(p.R));
+  if (t3) std::memcpy(t3, p.t, sizeof(p.t));
+}
+float mod_host_threshold_ge(double th) { return float_ceil_of_double(th); }
+float mod_host_threshold_gt(double th) { return float_floor_of_double(th); }
+float mod_host_sq_threshold(float thr) { return sq_threshold(thr); }
 
 void* mod_host_alloc(size_t bytes) {
   void* p = nullptr;

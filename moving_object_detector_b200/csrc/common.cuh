@@ -110,5 +110,6 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
 // float threshold equivalents of the reference's float-vs-double comparisons
 float float_ceil_of_double(double th);   // smallest float >= th
 float float_floor_of_double(double th);  // largest float <= th
+float sq_threshold(float thr);           // smallest float s2 with sqrtf(s2) >= thr
 
 }  // namespace mod

@@ -1,0 +1,97 @@
+"""Frame-pair sharding: partition arithmetic, and the one collective of the multi-GPU path -- the
+all-gather of per-frame object records -- exercised with two gloo ranks on the CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from moving_object_detector_b200 import OBJECT_DTYPE, STATS_DTYPE
+from moving_object_detector_b200.sharding import (merge_gathered, padded_block, shard_frames, shard_range)
+
+
+@pytest.mark.parametrize("n_pairs,world", [(1024, 8), (63, 2), (63, 4), (7, 8), (0, 2), (1, 1), (1000, 3)])
+def test_shards_are_a_contiguous_partition(n_pairs, world):
+    cover = []
+    sizes = []
+    for r in range(world):
+        a, b = shard_range(n_pairs, r, world)
+        assert 0 <= a <= b <= n_pairs
+        cover += list(range(a, b))
+        sizes.append(b - a)
+        fa, fb = shard_frames(n_pairs, r, world)
+        assert (fb - fa) == (b - a + 1 if b > a else 0)
+    assert cover == list(range(n_pairs))
+    assert max(sizes) - min(sizes) <= 1 and max(sizes) == padded_block(n_pairs, world)
+
+
+def test_bad_shard_requests_raise():
+    for args in ((10, 2, 2), (10, -1, 2), (10, 0, 0), (-1, 0, 1)):
+        with pytest.raises(ValueError):
+            shard_range(*args)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+MAX_OBJS = 4
+
+
+def _rank_records(rank, world, n_pairs):
+    """Deterministic fake clusterer output of one rank: pair g has (g % 3) objects whose id/centre encode g."""
+    first, last = shard_range(n_pairs, rank, world)
+    block = padded_block(n_pairs, world)
+    objs = np.zeros((block, MAX_OBJS), OBJECT_DTYPE)
+    stats = np.zeros(block, STATS_DTYPE)
+    for k, g in enumerate(range(first, last)):
+        n = g % 3
+        stats["n_objects"][k] = n
+        stats["n_clusters"][k] = n
+        for j in range(n):
+            objs[k, j]["id"] = j
+            objs[k, j]["center"] = (g, j, rank)
+            objs[k, j]["n_points"] = 100 + g
+    return objs, stats
+
+
+def _worker(rank, world, port, n_pairs, q):
+    import torch
+    import torch.distributed as dist
+    from moving_object_detector_b200.sharding import gather_object_lists
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        objs, stats = _rank_records(rank, world, n_pairs)
+        t_objs = torch.from_numpy(objs.view(np.uint8).reshape(objs.shape[0], -1).copy())
+        t_stats = torch.from_numpy(stats.view(np.uint8).reshape(stats.shape[0], -1).copy())
+        g_objs, g_stats = gather_object_lists(t_objs, t_stats)
+        merged = merge_gathered(g_objs.numpy(), g_stats.numpy(), n_pairs, OBJECT_DTYPE, STATS_DTYPE)
+        ok = len(merged) == n_pairs
+        for g, rec in enumerate(merged):
+            ok &= len(rec) == g % 3
+            ok &= all(int(r["n_points"]) == 100 + g and float(r["center"][0]) == g for r in rec)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_pairs", [7, 8])
+def test_object_list_all_gather_two_gloo_ranks(n_pairs):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_pairs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0, "a rank failed"
+    results = [q.get(timeout=10) for _ in procs]
+    assert sorted(results) == [(0, True), (1, True)]
