@@ -123,9 +123,10 @@ unsigned long long mod_launch_count(const mod_ctx* ctx);
 /* The context's own non-blocking stream (a cudaStream_t), usable as the `stream` argument of the *_dev calls. */
 void* mod_stream(const mod_ctx* ctx);
 
-/* Numerics self-check used by the tests: counts, into *d_n_bad, the operand pairs (d_a[i], d_b[i]) for which the kernel's
- * FP64-pipe float division differs bitwise from IEEE float division (__fdiv_rn, i.e. the reference's divss). */
-int mod_selfcheck_fdiv(mod_ctx* ctx, void* stream, const float* d_a, const float* d_b, size_t n,
+/* Numerics self-check used by the tests: counts, into *d_n_bad, the operand pairs (d_a[i], d_b[i]) for which the
+ * kernel's shared-reciprocal double division (one reciprocal per divisor Z / dt, scene_flow_constructor.cpp:84,200-202)
+ * differs bitwise from IEEE double division (__ddiv_rn, i.e. the reference's divsd). */
+int mod_selfcheck_ddiv(mod_ctx* ctx, void* stream, const double* d_a, const double* d_b, size_t n,
                        unsigned long long* d_n_bad);
 
 /* ---- O(1) host-side parameter preparation, exposed so the CPU test-suite can pin it without a GPU ---------- */

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmod_b200.so")
+# MOD_B200_LIB lets a developer point the harness at an experimental build of the same C ABI (kernel tuning sweeps)
+LIB_PATH = os.environ.get("MOD_B200_LIB") or os.path.join(_HERE, "libmod_b200.so")
 
 MOD_OK = 0
 MOD_ERR_INVALID_ARG = -1
@@ -86,7 +87,7 @@ PROTOTYPES = {
     "mod_last_error": (C.c_char_p, [C.c_void_p]),
     "mod_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mod_stream": (C.c_void_p, [C.c_void_p]),
-    "mod_selfcheck_fdiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mod_selfcheck_ddiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mod_host_rotation": (None, [C.POINTER(Transform), C.c_void_p, C.c_void_p]),
     "mod_host_threshold_ge": (C.c_float, [C.c_double]),
     "mod_host_threshold_gt": (C.c_float, [C.c_double]),

@@ -151,11 +151,11 @@ class Context:
         """The context's own cudaStream_t as an integer handle."""
         return int(self._lib.mod_stream(self._h) or 0)
 
-    def selfcheck_fdiv(self, a, b, stream: int = 0) -> int:
-        """a, b: float32 CUDA tensors.  Returns the number of pairs where the kernel's division differs from IEEE."""
+    def selfcheck_ddiv(self, a, b, stream: int = 0) -> int:
+        """a, b: float64 CUDA tensors.  Returns the number of pairs where the kernel's division differs from IEEE."""
         import torch
         bad = torch.zeros(1, dtype=torch.int64, device=a.device)
-        self._check(self._lib.mod_selfcheck_fdiv(self._h, stream or None, _dev_ptr(a), _dev_ptr(b), a.numel(),
+        self._check(self._lib.mod_selfcheck_ddiv(self._h, stream or None, _dev_ptr(a), _dev_ptr(b), a.numel(),
                                                  _dev_ptr(bad)))
         return int(bad.item())
 

@@ -145,6 +145,24 @@ void fill_transform(const mod_transform& m, SfPair& p) {
   p.t[2] = m.tz;
 }
 
+// Smallest previous-frame disparity for which isValid(pc_previous_transformed.at(previous)) (scene_flow_constructor.cpp
+// :187-189) is certain without evaluating the point: for 0 < d_safe <= d the depth f*T/d is at most z_max, and z_max is
+// chosen so that |R0 . (rx z, ry z, z) + t0| stays far below FLT_MAX with every intermediate finite.  Anything the
+// bound cannot cover (non-finite or negative f*T, non-finite transform or camera) yields +inf: the kernel then
+// evaluates the point for every pixel that reaches the gate.
+float safe_disparity(const SfPair& p, double ray_x_max, double ray_y_max) {
+  const double fT = static_cast<double>(p.fT_prev);
+  const double s = std::fabs(p.R[0]) * ray_x_max + std::fabs(p.R[1]) * ray_y_max + std::fabs(p.R[2]);
+  const double t0 = std::fabs(p.t[0]);
+  if (!(fT >= 0.0) || !std::isfinite(fT) || !std::isfinite(s) || !std::isfinite(t0) || !std::isfinite(ray_x_max) ||
+      !std::isfinite(ray_y_max) || t0 > 1e30 || s > 1e30 || ray_x_max > 1e30 || ray_y_max > 1e30)
+    return INFINITY;
+  const double z_max = 1e30 / (s + ray_x_max + ray_y_max + 1.0);  // |x|,|y|,|z|,|m.x| <= ~1e30 + 1e30 << FLT_MAX
+  double d = 4.0 * fT / z_max;                                    // float rounding of f*T/d is covered by the factor 4
+  if (!(d > 1e-30)) d = 1e-30;                                    // stay clear of subnormal float disparities
+  return mod::float_ceil_of_double(d);
+}
+
 bool same_camera(const mod_camera& a, const mod_camera& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
 
 int ensure_lut(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_camera& cam) {
@@ -185,8 +203,14 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
   L.Ty = cam.Ty;
   L.w = w;
   L.h = h;
-  L.flow_diff_thr = static_cast<float>(params.dynamic_flow_diff);  // float >= int promotes the int (cpp:198)
-  L.speed_thr = float_ceil_of_double(dynamic_speed);
+  // std::sqrt(s) >= dynamic_flow_diff_: the int is promoted to float (cpp:198); sqrt-free form, see sq_threshold
+  L.flow_thr2 = sq_threshold(static_cast<float>(params.dynamic_flow_diff));
+  // (double)norm >= dynamic_speed_th_  <=>  norm >= ceil_float(th)  <=>  norm^2 >= sq_threshold(ceil_float(th))
+  L.speed_thr2 = sq_threshold(float_ceil_of_double(dynamic_speed));
+  // |ray| is largest at an image border (the ray is affine in the pixel coordinate)
+  const double rx0 = std::fabs((0.0 - cam.cx - cam.Tx) / cam.fx), rx1 = std::fabs((w - 1.0 - cam.cx - cam.Tx) / cam.fx);
+  const double ry0 = std::fabs((0.0 - cam.cy - cam.Ty) / cam.fy), ry1 = std::fabs((h - 1.0 - cam.cy - cam.Ty) / cam.fy);
+  const double ray_x_max = 1.001 * (rx0 > rx1 ? rx0 : rx1), ray_y_max = 1.001 * (ry0 > ry1 ? ry0 : ry1);
   L.points = d_points;
   L.points_frame_stride = frame_stride_points;
   L.mask = d_mask;
@@ -208,6 +232,8 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
       p.fT_prev = src.f_prev * src.T_prev;
       p.min_prev = src.min_disparity_prev;
       p.max_prev = src.max_disparity_prev;
+      p.d_safe = safe_disparity(p, ray_x_max, ray_y_max);
+      p.pad = 0.0f;
     }
     L.first_frame = first;
     MOD_CK(ctx, launch_scene_flow(s, L, n));
@@ -368,11 +394,11 @@ const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null c
 
 unsigned long long mod_launch_count(const mod_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int mod_selfcheck_fdiv(mod_ctx* ctx, void* stream, const float* d_a, const float* d_b, size_t n,
+int mod_selfcheck_ddiv(mod_ctx* ctx, void* stream, const double* d_a, const double* d_b, size_t n,
                        unsigned long long* d_n_bad) {
   if (!ctx || !d_a || !d_b || !d_n_bad) return MOD_ERR_INVALID_ARG;
   MOD_CK(ctx, cudaSetDevice(ctx->device));
-  MOD_CK(ctx, launch_fdiv_check(static_cast<cudaStream_t>(stream), d_a, d_b, n, d_n_bad));
+  MOD_CK(ctx, launch_ddiv_check(static_cast<cudaStream_t>(stream), d_a, d_b, n, d_n_bad));
   ctx->launches++;
   return MOD_OK;
 }

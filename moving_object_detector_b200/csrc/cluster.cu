@@ -69,6 +69,17 @@ __device__ __forceinline__ int uf_find(int* parent, int i) {
   }
 }
 
+// Read-only find (no path compression).  cl_roots must use this one: a path-halving store issued from a stale read
+// may land AFTER another thread has stored that node's final root and silently replace it by an intermediate
+// ancestor, which breaks the "pixel -> tile root -> final root" two-hop invariant the later kernels rely on.
+__device__ __forceinline__ int uf_find_readonly(const int* parent, int i) {
+  for (;;) {
+    const int p = __ldcg(parent + i);
+    if (p == i) return i;
+    i = p;
+  }
+}
+
 // Lock-free union: the larger root is pointed at the smaller one with atomicMin; on interference retry from the
 // value that was found there.
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
@@ -193,6 +204,15 @@ __device__ __forceinline__ int smem_find(volatile int* lab, int i) {
     if (gp == p) return p;
     lab[i] = gp;
     i = gp;
+  }
+}
+// Read-only variant for the flatten pass (D1): there every thread stores the ROOT of its own pixel, and a
+// path-halving store from a stale read could overwrite that root with an intermediate ancestor afterwards.
+__device__ __forceinline__ int smem_find_readonly(const volatile int* lab, int i) {
+  for (;;) {
+    const int p = lab[i];
+    if (p == i) return i;
+    i = p;
   }
 }
 __device__ __forceinline__ void smem_union(int* lab, int a, int b) {
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(kBlock)
     int c = 0;
     if (e < nd) {
       c = s_dl[e];
-      const int r = smem_find(s_lab, c);
+      const int r = smem_find_readonly(s_lab, c);  // no halving stores here: see smem_find_readonly
       s_lab[c] = r;
       is_root = (r == c);
       if (is_root) {
@@ -616,9 +636,9 @@ __global__ void __launch_bounds__(kBlock)
       const uint32_t frame = g / P;
       const int r = static_cast<int>(g - frame * P);
       int* parent = L.parent + static_cast<size_t>(frame) * P;
-      const int R = uf_find(parent, r);
+      const int R = uf_find_readonly(parent, r);  // every store of this kernel writes a final root: no races
       if (R != r) {
-        parent[r] = R;
+        __stcg(parent + r, R);
         const size_t gR = static_cast<size_t>(frame) * P + R;
         const TileStat src = L.tstat[g];
         TileStat& dst = L.tstat[gR];

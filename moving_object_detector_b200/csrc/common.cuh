@@ -22,9 +22,11 @@ struct SfPair {
   double dt;               // (stamp_now - stamp_prev).toSec()
   float fT_now, min_now, max_now;     // f*T evaluated in float as at disparity_image_processor.cpp:43
   float fT_prev, min_prev, max_prev;
+  float d_safe;            // previous disparities >= d_safe are known to ego-transform to a finite, non-NaN x
+  float pad;
 };
 
-constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 160 B = 10 KB of the 32 KB parameter space
+constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 168 B = 10.5 KB of the 32 KB parameter space
 
 struct SfLaunch {
   SfPair pair[kSfMaxPairsPerLaunch];
@@ -32,8 +34,8 @@ struct SfLaunch {
   const double* ray_y;  // [h]  ((double)v - cy - Ty) / fy
   double fx, fy, cx, cy, Tx, Ty;
   int w, h;
-  float flow_diff_thr;   // (float)dynamic_flow_diff
-  float speed_thr;       // smallest float >= dynamic_speed   ((double)a >= th  <=>  a >= th_up)
+  float flow_thr2;       // sqrtf(s) >= (float)dynamic_flow_diff  <=>  s >= flow_thr2   (sq_threshold)
+  float speed_thr2;      // (double)sqrtf(s) >= dynamic_speed     <=>  s >= speed_thr2
   float* points;         // 8 floats per point
   size_t points_frame_stride;  // in points
   uint8_t* mask;         // may be null
@@ -89,7 +91,7 @@ struct ClusterStat {
 
 void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, int w, int h, const mod_camera& cam);
 cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs);
-cudaError_t launch_fdiv_check(cudaStream_t s, const float* a, const float* b, size_t n, unsigned long long* n_bad);
+cudaError_t launch_ddiv_check(cudaStream_t s, const double* a, const double* b, size_t n, unsigned long long* n_bad);
 cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame_stride_points, uint8_t* mask, int w,
                                int h, int batch, float speed_thr);
 // Workspaces of the clusterer that are not indexed per pixel in ClLaunch.

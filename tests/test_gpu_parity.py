@@ -70,3 +70,19 @@ def test_pipeline_fused_matches_oracle(ctx, oracle, gazebo_seq):
     want = oracle.cluster(want_sf["points32"])
     assert np.array_equal(res.labels, want["labels"])
     assert_objects_match(res.objects, want["objects"], want_sf["points32"], want["labels"])
+
+
+def test_cluster_long_root_chains_are_repeatable(oracle):
+    """Regression: a frame-spanning serpentine at N=1 builds long chains of tile roots; a path-halving store in
+    cl_roots used to race with the final-root store and misroute a few member pixels (flaky median).  Fresh contexts
+    and repeated calls must give the oracle's objects every time."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cl_stress_n1.npz"))
+    cloud = np.ascontiguousarray(g["points32"])
+    cfg = ClustererConfig(int(g["params"][0]), float(g["thresholds"][0]), float(g["thresholds"][1]), 1)
+    for trial in range(25):
+        with Context(256, 192, max_batch=1) as c:
+            for rep in range(2):
+                got = c.cluster(cloud, cfg)
+                assert np.array_equal(got.labels, g["labels"]), f"trial {trial} rep {rep}"
+                assert_objects_match(got.objects, g["objects"], cloud, g["labels"])
