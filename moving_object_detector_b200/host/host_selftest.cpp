@@ -1,0 +1,134 @@
+// host_selftest.cpp -- drives the C++ host classes the way the ROS callbacks would.
+//   host_selftest --no-gpu                     checks that construction fails loudly without a GPU, the PointCloud2
+//                                              description and ros::Time arithmetic (runs in the CPU test-suite)
+//   host_selftest <case.bin> <out.bin>         runs construct() -> ~scene_flow -> dataCB() -> ~moving_objects on one
+//                                              frame pair read from case.bin and writes cloud + objects (GPU tests
+//                                              compare them with the oracle)
+// case.bin: int32 w,h ; double cam[6] (fx,fy,cx,cy,Tx,Ty) ; float f,T,min,max ; double tr[7] ; uint32 sec0,nsec0,sec1,nsec1 ;
+//           int32 dynamic_flow_diff, cluster_size ; double depth_diff, dynamic_speed ; int32 neighbor_distance, pad ;
+//           float disp_prev[w*h], disp_now[w*h], flow[w*h*2]
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "scene_flow_host.h"
+
+namespace sfc = scene_flow_constructor;
+namespace cl = scene_flow_clusterer;
+
+static int fail(const char* what) {
+  std::fprintf(stderr, "host_selftest: FAILED: %s\n", what);
+  return 1;
+}
+
+static int runNoGpu() {
+  sensor_msgs::PointCloud2 pc;
+  sfc::describeVelocityCloud(pc, 7, 3);
+  if (pc.point_step != 32 || pc.row_step != 224 || pc.fields.size() != 6 || pc.fields[3].name != "vx" ||
+      pc.fields[3].offset != 16 || pc.fields[5].offset != 24 || !pc.is_dense)
+    return fail("PointCloud2 description");
+  ros::Time a, b;
+  a.sec = 10; a.nsec = 100000000;
+  b.sec = 9;  b.nsec = 900000000;
+  if (std::fabs((a - b).toSec() - 0.2) > 1e-12) return fail("ros::Time difference");
+  try {
+    sfc::SceneFlowConstructorB200 c(64, 64, 0);
+    std::printf("host_selftest: a GPU is present; --no-gpu checks skipped construction failure\n");
+  } catch (const std::runtime_error& e) {
+    std::printf("host_selftest: construction refused as expected: %s\n", e.what());
+  }
+  std::printf("host_selftest: no-gpu checks ok\n");
+  return 0;
+}
+
+template <typename T>
+static bool readv(FILE* f, T* p, size_t n) { return std::fread(p, sizeof(T), n, f) == n; }
+
+int main(int argc, char** argv) {
+  if (argc == 2 && std::strcmp(argv[1], "--no-gpu") == 0) return runNoGpu();
+  if (argc != 3) return fail("usage: host_selftest --no-gpu | <case.bin> <out.bin>");
+  FILE* f = std::fopen(argv[1], "rb");
+  if (!f) return fail("cannot open case file");
+  int32_t wh[2], ip[2], nd[2];
+  double cam[6], tr[7], th[2];
+  float meta[4];
+  uint32_t stamps[4];
+  if (!readv(f, wh, 2) || !readv(f, cam, 6) || !readv(f, meta, 4) || !readv(f, tr, 7) || !readv(f, stamps, 4) ||
+      !readv(f, ip, 2) || !readv(f, th, 2) || !readv(f, nd, 2))
+    return fail("short case header");
+  const uint32_t w = wh[0], h = wh[1];
+  const size_t P = static_cast<size_t>(w) * h;
+  auto mkdisp = [&](uint32_t sec, uint32_t nsec) {
+    auto d = std::make_shared<stereo_msgs::DisparityImage>();
+    d->header.stamp.sec = sec;
+    d->header.stamp.nsec = nsec;
+    d->image.width = w;
+    d->image.height = h;
+    d->image.encoding = "32FC1";
+    d->image.step = w * 4;
+    d->image.data.resize(P * 4);
+    d->f = meta[0]; d->T = meta[1]; d->min_disparity = meta[2]; d->max_disparity = meta[3];
+    return d;
+  };
+  auto prev = mkdisp(stamps[0], stamps[1]), now = mkdisp(stamps[2], stamps[3]);
+  auto flow = std::make_shared<sensor_msgs::Image>();
+  flow->header = now->header;
+  flow->width = w; flow->height = h; flow->encoding = "32FC2"; flow->step = w * 8;
+  flow->data.resize(P * 8);
+  if (!readv(f, prev->image.data.data(), P * 4) || !readv(f, now->image.data.data(), P * 4) ||
+      !readv(f, flow->data.data(), P * 8))
+    return fail("short case payload");
+  std::fclose(f);
+  auto transform = std::make_shared<geometry_msgs::Transform>();
+  transform->translation.x = tr[0]; transform->translation.y = tr[1]; transform->translation.z = tr[2];
+  transform->rotation.x = tr[3]; transform->rotation.y = tr[4]; transform->rotation.z = tr[5]; transform->rotation.w = tr[6];
+  sensor_msgs::CameraInfo info;
+  info.width = w; info.height = h;
+  info.P = {cam[0], 0, cam[2], cam[4], 0, cam[1], cam[3], cam[5], 0, 0, 1, 0};
+  info.header.frame_id = "left_camera";
+
+  try {
+    sfc::SceneFlowConstructorB200 constructor(static_cast<int>(w), static_cast<int>(h));
+    cl::ClustererB200 clusterer(static_cast<int>(w), static_cast<int>(h));
+    constructor.reconfigureCB(sfc::SceneFlowConstructorConfig{ip[0], 1.0}, 0);
+    clusterer.reconfigureCB(cl::ClustererConfig{ip[1], th[0], th[1], nd[0]}, 0);
+    constructor.setCameraInfo(info);
+
+    // degrade rules first: nothing may be published without flow / previous frame / transform
+    int published = 0;
+    constructor.pc_with_velocity_pub_.publish = [&](const sensor_msgs::PointCloud2&) { published++; };
+    constructor.pc_with_velocity_pub_.num_subscribers = 1;
+    if (constructor.construct(now, prev, nullptr, transform) || published) return fail("published without flow");
+    if (constructor.construct(now, nullptr, flow, transform) || published) return fail("published without previous frame");
+    if (constructor.construct(now, prev, flow, nullptr) || published) return fail("published without transform");
+
+    sensor_msgs::PointCloud2 cloud;
+    moving_object_msgs::MovingObjectArray objects;
+    bool got_objects = false;
+    constructor.pc_with_velocity_pub_.publish = [&](const sensor_msgs::PointCloud2& m) { cloud = m; published++; };
+    clusterer.dynamic_objects_pub_.publish = [&](const moving_object_msgs::MovingObjectArray& m) { objects = m; got_objects = true; };
+    clusterer.dynamic_objects_pub_.num_subscribers = 1;
+    if (!constructor.construct(now, prev, flow, transform)) return fail(constructor.lastError().c_str());
+    if (published != 1 || cloud.data.size() != P * 32) return fail("~scene_flow not published");
+    if (!clusterer.dataCB(cloud)) return fail(clusterer.lastError().c_str());
+    if (!got_objects) return fail("~moving_objects not published");
+
+    FILE* o = std::fopen(argv[2], "wb");
+    if (!o) return fail("cannot open output file");
+    const int32_t n = static_cast<int32_t>(objects.moving_object_array.size());
+    std::fwrite(cloud.data.data(), 1, cloud.data.size(), o);
+    std::fwrite(&n, sizeof(n), 1, o);
+    for (const auto& m : objects.moving_object_array) {
+      const double rec[10] = {static_cast<double>(m.id), m.center.position.x, m.center.position.y, m.center.position.z,
+                              m.velocity.x, m.velocity.y, m.velocity.z, m.bounding_box.x, m.bounding_box.y, m.bounding_box.z};
+      std::fwrite(rec, sizeof(double), 10, o);
+    }
+    std::fclose(o);
+    std::printf("host_selftest: ok, %d moving objects\n", n);
+  } catch (const std::exception& e) {
+    return fail(e.what());
+  }
+  return 0;
+}

@@ -1,0 +1,243 @@
+// scene_flow_host.cpp -- see scene_flow_host.h.  Host logic only; every computation is one C-ABI call.
+#include "scene_flow_host.h"
+
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace {
+
+std::string ctxError(mod_ctx* ctx, const char* what, int rc) {
+  return std::string(what) + " failed (" + std::to_string(rc) + "): " + (ctx ? mod_last_error(ctx) : "no context");
+}
+
+mod_ctx* createContext(int max_w, int max_h, int device) {
+  mod_ctx* ctx = nullptr;
+  const int rc = mod_create(device, max_w, max_h, 1, 0, &ctx);
+  if (rc != MOD_OK)
+    throw std::runtime_error("mod_create failed (" + std::to_string(rc) +
+                             "): no usable sm_100a GPU; this path has no CPU fallback");
+  return ctx;
+}
+
+mod_disparity toC(const stereo_msgs::DisparityImage& d) {
+  mod_disparity c;
+  c.f = d.f;
+  c.T = d.T;
+  c.min_disparity = d.min_disparity;
+  c.max_disparity = d.max_disparity;
+  c.data = reinterpret_cast<const float*>(d.image.data.data());  // cv::Mat_<float>(h, w, data, step), dip.cpp:5
+  c.step_bytes = static_cast<int32_t>(d.image.step);
+  return c;
+}
+
+void fillImage(sensor_msgs::Image& img, const std_msgs::Header& header, uint32_t w, uint32_t h, const char* encoding,
+               uint32_t bytes_per_pixel) {
+  img.header = header;
+  img.width = w;
+  img.height = h;
+  img.encoding = encoding;
+  img.is_bigendian = 0;
+  img.step = w * bytes_per_pixel;
+  img.data.resize(static_cast<size_t>(img.step) * h);
+}
+
+}  // namespace
+
+namespace scene_flow_constructor {
+
+SceneFlowConstructorB200::SceneFlowConstructorB200(int max_w, int max_h, int device)
+    : ctx_(createContext(max_w, max_h, device)) {}
+
+SceneFlowConstructorB200::~SceneFlowConstructorB200() { mod_destroy(ctx_); }
+
+void SceneFlowConstructorB200::reconfigureCB(const SceneFlowConstructorConfig& config, uint32_t /*level*/) {
+  dynamic_flow_diff_ = config.dynamic_flow_diff;
+  max_color_velocity_ = config.max_color_velocity;
+}
+
+void SceneFlowConstructorB200::setCameraInfo(const sensor_msgs::CameraInfo& info) {
+  // image_geometry::PinholeCameraModel::fromCameraInfo: P is copied, then adjusted for ROI offset and binning
+  // (no-ops for binning 0/1 and a zero ROI, which is what image_crop emits: image_crop.cpp:32-38)
+  const double bx = info.binning_x == 0 ? 1.0 : static_cast<double>(info.binning_x);
+  const double by = info.binning_y == 0 ? 1.0 : static_cast<double>(info.binning_y);
+  double fx = info.P[0], fy = info.P[5], cx = info.P[2], cy = info.P[6], Tx = info.P[3], Ty = info.P[7];
+  cx -= info.roi.x_offset;
+  cy -= info.roi.y_offset;
+  if (bx > 1.0) { fx /= bx; cx /= bx; Tx /= bx; }
+  if (by > 1.0) { fy /= by; cy /= by; Ty /= by; }
+  camera_ = mod_camera{fx, fy, cx, cy, Tx, Ty};
+  camera_frame_id_ = info.header.frame_id;
+  have_camera_ = true;
+}
+
+void describeVelocityCloud(sensor_msgs::PointCloud2& msg, uint32_t width, uint32_t height) {
+  static const char* names[6] = {"x", "y", "z", "vx", "vy", "vz"};
+  static const uint32_t offsets[6] = {0, 4, 8, 16, 20, 24};
+  msg.fields.resize(6);
+  for (int i = 0; i < 6; i++) {
+    msg.fields[i].name = names[i];
+    msg.fields[i].offset = offsets[i];
+    msg.fields[i].datatype = sensor_msgs::PointField::FLOAT32;
+    msg.fields[i].count = 1;
+  }
+  msg.width = width;
+  msg.height = height;
+  msg.is_bigendian = false;
+  msg.point_step = 32;
+  msg.row_step = 32 * width;
+  msg.is_dense = true;  // pcl::PointCloud(w, h, value) leaves is_dense = true although the cloud holds NaN
+}
+
+bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_now,
+                                         const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_previous,
+                                         const std::shared_ptr<const sensor_msgs::Image>& left_flow,
+                                         const std::shared_ptr<const geometry_msgs::Transform>& transform_prev2now) {
+  last_error_.clear();
+  if (left_flow && optflow_pub_.getNumSubscribers() > 0) optflow_pub_.publish(*left_flow);  // :99-100
+
+  const bool full = disparity_now && disparity_previous && left_flow && transform_prev2now && have_camera_;
+  const bool want_depth = disparity_now && depth_pub_.getNumSubscribers() > 0 && have_camera_;
+
+  if (!full) {
+    // ~depth alone (:111-119): the reference publishes it before the left_flow gate (:122-123).  The kernel needs a
+    // full pair, so the depth image is produced by pairing the frame with itself under an identity transform; the
+    // depth output only depends on disparity_now (disparity_image_processor.cpp:105-121).
+    if (!want_depth) return false;
+    const uint32_t w = disparity_now->image.width, h = disparity_now->image.height;
+    std::vector<float> zero_flow(static_cast<size_t>(w) * h * 2, 0.0f);
+    sensor_msgs::Image depth;
+    std_msgs::Header hd;
+    hd.frame_id = camera_frame_id_;
+    hd.stamp = disparity_now->header.stamp;  // publishDepthImage(:431-438)
+    fillImage(depth, hd, w, h, "32FC1", 4);
+    const mod_disparity now = toC(*disparity_now);
+    const mod_transform ident{0, 0, 0, 0, 0, 0, 1};
+    const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
+    const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &now,
+                                  zero_flow.data(), static_cast<int32_t>(w * 8), &ident, 1.0, &p, nullptr,
+                                  reinterpret_cast<float*>(depth.data.data()), nullptr);
+    if (rc != MOD_OK) {
+      last_error_ = ctxError(ctx_, "mod_scene_flow(depth)", rc);
+      return false;
+    }
+    depth_pub_.publish(depth);
+    return false;
+  }
+
+  const uint32_t w = disparity_now->image.width, h = disparity_now->image.height;
+  if (disparity_previous->image.width != w || disparity_previous->image.height != h || left_flow->width != w ||
+      left_flow->height != h) {
+    last_error_ = "frame size mismatch between disparity_now, disparity_previous and left_flow";
+    return false;
+  }
+  const bool want_cloud = pc_with_velocity_pub_.getNumSubscribers() > 0;    // :141
+  const bool want_static = static_flow_pub_.getNumSubscribers() > 0;        // :144
+
+  sensor_msgs::PointCloud2 cloud;
+  sensor_msgs::Image depth, static_flow;
+  if (want_cloud) {
+    describeVelocityCloud(cloud, w, h);
+    cloud.header = left_flow->header;  // publishPointcloud(..., left_flow->header), :142
+    cloud.data.resize(static_cast<size_t>(w) * h * 32);
+  }
+  if (want_depth) {
+    std_msgs::Header hd;
+    hd.frame_id = camera_frame_id_;
+    hd.stamp = disparity_now->header.stamp;
+    fillImage(depth, hd, w, h, "32FC1", 4);
+  }
+  if (want_static) fillImage(static_flow, left_flow->header, w, h, "32FC2", 8);
+
+  const mod_disparity now = toC(*disparity_now), prev = toC(*disparity_previous);
+  const geometry_msgs::Transform& t = *transform_prev2now;
+  const mod_transform tr{t.translation.x, t.translation.y, t.translation.z, t.rotation.x, t.rotation.y, t.rotation.z,
+                         t.rotation.w};
+  // (stamp_now - stamp_previous).toSec(), :162-164
+  const double dt = (disparity_now->header.stamp - disparity_previous->header.stamp).toSec();
+  const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
+  const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &prev,
+                                reinterpret_cast<const float*>(left_flow->data.data()),
+                                static_cast<int32_t>(left_flow->step), &tr, dt, &p,
+                                want_cloud ? cloud.data.data() : nullptr,
+                                want_depth ? reinterpret_cast<float*>(depth.data.data()) : nullptr,
+                                want_static ? reinterpret_cast<float*>(static_flow.data.data()) : nullptr);
+  if (rc != MOD_OK) {
+    last_error_ = ctxError(ctx_, "mod_scene_flow", rc);
+    return false;
+  }
+  if (want_depth) depth_pub_.publish(depth);
+  if (want_cloud) pc_with_velocity_pub_.publish(cloud);
+  if (want_static) static_flow_pub_.publish(static_flow);
+  return true;
+}
+
+}  // namespace scene_flow_constructor
+
+namespace scene_flow_clusterer {
+
+ClustererB200::ClustererB200(int max_w, int max_h, int device) : ctx_(createContext(max_w, max_h, device)) {}
+ClustererB200::~ClustererB200() { mod_destroy(ctx_); }
+
+void ClustererB200::reconfigureCB(const ClustererConfig& config, uint32_t /*level*/) {
+  cluster_size_th_ = config.cluster_size;
+  depth_diff_th_ = config.depth_diff;
+  dynamic_speed_th_ = config.dynamic_speed;
+  neighbor_distance_th_ = config.neighbor_distance;
+}
+
+bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
+  last_error_.clear();
+  if (dynamic_objects_pub_.getNumSubscribers() <= 0) return true;  // nothing else on the hot path is subscribed
+  // pcl::fromROSMsg maps fields by name; the constructor's cloud is the 32-byte record x@0 y@4 z@8 vx@16 vy@20 vz@24
+  if (msg.point_step != 32 || msg.row_step != 32u * msg.width ||
+      msg.data.size() < static_cast<size_t>(msg.row_step) * msg.height) {
+    last_error_ = "scene_flow cloud is not an organized PointXYZVelocity cloud with point_step 32";
+    return false;
+  }
+  static const char* names[6] = {"x", "y", "z", "vx", "vy", "vz"};
+  static const uint32_t offsets[6] = {0, 4, 8, 16, 20, 24};
+  for (int i = 0; i < 6; i++) {
+    bool found = false;
+    for (const auto& f : msg.fields)
+      found = found || (f.name == names[i] && f.offset == offsets[i] && f.datatype == sensor_msgs::PointField::FLOAT32);
+    if (!found) {
+      last_error_ = std::string("scene_flow cloud lacks FLOAT32 field ") + names[i] + " at the expected offset";
+      return false;
+    }
+  }
+  const mod_cl_params p{cluster_size_th_, depth_diff_th_, dynamic_speed_th_, neighbor_distance_th_};
+  std::vector<mod_object> objs(4096);
+  int32_t n = 0;
+  const int rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), msg.data.data(), &p,
+                             nullptr, objs.data(), static_cast<int32_t>(objs.size()), &n);
+  if (rc != MOD_OK) {
+    last_error_ = ctxError(ctx_, "mod_cluster", rc);
+    return false;
+  }
+  moving_object_msgs::MovingObjectArray out;
+  out.header = msg.header;  // moving_objects_msg.header = input_header_, :327
+  out.moving_object_array.resize(static_cast<size_t>(n));
+  for (int32_t i = 0; i < n; i++) {
+    const mod_object& o = objs[static_cast<size_t>(i)];
+    moving_object_msgs::MovingObject& m = out.moving_object_array[static_cast<size_t>(i)];
+    m.id = o.id;
+    m.center.position.x = o.center[0];  // float -> float64, as the reference's assignments do (:151-181)
+    m.center.position.y = o.center[1];
+    m.center.position.z = o.center[2];
+    m.center.orientation.x = 0;
+    m.center.orientation.y = 0;
+    m.center.orientation.z = 0;
+    m.center.orientation.w = 1;
+    m.velocity.x = o.velocity[0];
+    m.velocity.y = o.velocity[1];
+    m.velocity.z = o.velocity[2];
+    m.bounding_box.x = o.bbox[0];
+    m.bounding_box.y = o.bbox[1];
+    m.bounding_box.z = o.bbox[2];
+  }
+  dynamic_objects_pub_.publish(out);
+  return true;
+}
+
+}  // namespace scene_flow_clusterer

@@ -1,0 +1,126 @@
+// scene_flow_host.h -- C++ host side of the B200 path: the two classes a ROS maintainer swaps in for the reference's
+// compute methods.  They keep the reference's names, parameters, degrade rules and message layouts and call the GPU
+// only through the C ABI of include/mod_b200.h (no CUDA types here; link with -lmod_b200).
+//
+//   scene_flow_constructor::SceneFlowConstructorB200::construct()   <- SceneFlowConstructor::construct
+//        scene_flow_constructor/src/scene_flow_constructor.cpp:91-147 (+ :149-212, :65-89, :409-429 and
+//        disparity_image_proc/src/disparity_image_processor.cpp:86-121, all inside ONE mod_scene_flow / mod_pipeline call)
+//   scene_flow_clusterer::ClustererB200::dataCB()                   <- ClustererNodelet::dataCB
+//        scene_flow_clusterer/src/clusterer_nodelet.cpp:221-242 (clustering :85-95 + publishMovingObjects :324-343)
+//
+// ROS plumbing (NodeHandle, message_filters, image_transport, dynamic_reconfigure servers, nodelet/pluginlib export)
+// stays exactly as in the reference and is not duplicated here: INTEGRATION.md shows the few lines that change in
+// scene_flow_constructor.cpp / clusterer_nodelet.cpp.  "Publishers" are modelled as sinks with a subscriber count so
+// that the reference's getNumSubscribers() gating is preserved.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+
+#include "../../include/mod_b200.h"
+#include "ros_compat.h"
+
+namespace scene_flow_constructor {
+
+// cfg/SceneFlowConstructor.cfg:8-9 (generated SceneFlowConstructorConfig has exactly these two members)
+struct SceneFlowConstructorConfig {
+  int dynamic_flow_diff = 5;
+  double max_color_velocity = 1.0;
+};
+
+template <typename Msg>
+struct Sink {  // ros::Publisher stand-in: publish() + getNumSubscribers()
+  std::function<void(const Msg&)> publish;
+  int num_subscribers = 0;
+  int getNumSubscribers() const { return publish ? num_subscribers : 0; }
+};
+
+class SceneFlowConstructorB200 {
+ public:
+  // max_w / max_h size the device workspaces; device = CUDA ordinal.  Throws std::runtime_error when no sm_100a GPU
+  // is usable (there is no CPU fallback).
+  SceneFlowConstructorB200(int max_w, int max_h, int device = 0);
+  ~SceneFlowConstructorB200();
+  SceneFlowConstructorB200(const SceneFlowConstructorB200&) = delete;
+  SceneFlowConstructorB200& operator=(const SceneFlowConstructorB200&) = delete;
+
+  // dynamic_reconfigure callback (scene_flow_constructor.cpp:401-407): latches the two parameters
+  void reconfigureCB(const SceneFlowConstructorConfig& config, uint32_t level);
+
+  // left CameraInfo as latched at scene_flow_constructor.cpp:368-374 (PinholeCameraModel::fromCameraInfo: binning
+  // and ROI offsets are applied to P exactly as image_geometry does)
+  void setCameraInfo(const sensor_msgs::CameraInfo& left_camera_info);
+
+  // Same contract as SceneFlowConstructor::construct (:91-147): any argument may be null.
+  //   ~optical_flow is published whenever left_flow is set and subscribed           (:99-100)
+  //   ~depth needs disparity_now and a subscriber                                     (:111-119)
+  //   nothing else happens without left_flow                                          (:122-123)
+  //   ~scene_flow / ~synthetic_optical_flow need disparity_now, disparity_previous and transform_prev2now (:127-146)
+  // Returns true when the scene-flow cloud was computed (whether or not anybody subscribed to it).
+  bool construct(const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_now,
+                 const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_previous,
+                 const std::shared_ptr<const sensor_msgs::Image>& left_flow /* 32FC2 */,
+                 const std::shared_ptr<const geometry_msgs::Transform>& transform_prev2now);
+
+  Sink<sensor_msgs::Image> optflow_pub_;          // ~optical_flow            32FC2
+  Sink<sensor_msgs::Image> depth_pub_;            // ~depth                   32FC1
+  Sink<sensor_msgs::PointCloud2> pc_with_velocity_pub_;  // ~scene_flow       PointXYZVelocity, point_step 32
+  Sink<sensor_msgs::Image> static_flow_pub_;      // ~synthetic_optical_flow  32FC2
+
+  const std::string& lastError() const { return last_error_; }
+  mod_ctx* context() const { return ctx_; }
+
+ private:
+  mod_ctx* ctx_ = nullptr;
+  int dynamic_flow_diff_ = 5;
+  double max_color_velocity_ = 1.0;
+  bool have_camera_ = false;
+  mod_camera camera_{};
+  std::string camera_frame_id_;
+  std::string last_error_;
+};
+
+// pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZVelocity>) layout (pcl_point_xyz_velocity.h:8-34): fills everything
+// except `data` (which the GPU path writes directly) for an organized w x h cloud.
+void describeVelocityCloud(sensor_msgs::PointCloud2& msg, uint32_t width, uint32_t height);
+
+}  // namespace scene_flow_constructor
+
+namespace scene_flow_clusterer {
+
+// cfg/Clusterer.cfg:8-11
+struct ClustererConfig {
+  int cluster_size = 2500;
+  double depth_diff = 0.15;
+  double dynamic_speed = 0.3;
+  int neighbor_distance = 4;
+};
+
+class ClustererB200 {
+ public:
+  ClustererB200(int max_w, int max_h, int device = 0);
+  ~ClustererB200();
+  ClustererB200(const ClustererB200&) = delete;
+  ClustererB200& operator=(const ClustererB200&) = delete;
+
+  void reconfigureCB(const ClustererConfig& config, uint32_t level);  // clusterer_nodelet.cpp:345-352
+
+  // ClustererNodelet::dataCB (:221-242): ~moving_objects is computed and published when subscribed (:237-238).
+  // ~clusters / ~clusters_image are debug visualisations outside the hot path.
+  // Returns false (and publishes nothing) on a malformed cloud or a GPU error.
+  bool dataCB(const sensor_msgs::PointCloud2& input_pc_msg);
+
+  scene_flow_constructor::Sink<moving_object_msgs::MovingObjectArray> dynamic_objects_pub_;
+
+  const std::string& lastError() const { return last_error_; }
+
+ private:
+  mod_ctx* ctx_ = nullptr;
+  int cluster_size_th_ = 2500;
+  double depth_diff_th_ = 0.15;
+  double dynamic_speed_th_ = 0.3;
+  int neighbor_distance_th_ = 4;
+  std::string last_error_;
+};
+
+}  // namespace scene_flow_clusterer
