@@ -239,8 +239,8 @@ def main_ours(args):
     mask = torch.empty((B, P), dtype=torch.uint8, device=dev)
     objs = torch.zeros((B, MAX_OBJS * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world,) + tuple(objs.shape), dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered_stats = torch.empty((world,) + tuple(stats.shape), dtype=torch.uint8, device=dev) if world > 1 else None
+    from moving_object_detector_b200.sharding import gather_object_lists
+    gathered = None
     stream = torch.cuda.current_stream().cuda_stream
 
     sf_events = []
@@ -254,9 +254,9 @@ def main_ours(args):
             e1.record()
             sf_events.append((e0, e1))
         ctx.cluster_batched_dev(W, H, B, points, mask, cl_cfg, objs, stats, MAX_OBJS, stream=stream)
-        if world > 1:  # the only collective: per-frame object lists (never pixel data)
-            dist.all_gather_into_tensor(gathered, objs)
-            dist.all_gather_into_tensor(gathered_stats, stats)
+        if world > 1:  # the only collective: per-frame object lists (never pixel data), SURVEY.md 8(e)
+            nonlocal gathered
+            gathered = gather_object_lists(objs, stats)
 
     def barrier():
         if world > 1:
