@@ -196,6 +196,15 @@ int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch,
                             size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params* params,
                             int32_t* d_opt_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats);
 
+/* ---- static-flow filter (diagnostics) ------------------------------------------------------------------------ */
+/* The scene-flow kernel decides the residual gate (scene_flow_constructor.cpp:191-198) from a float evaluation of
+ * the static flow with a rigorous error bound and re-evaluates undecided pixels with the reference's exact
+ * arithmetic, so outputs do not depend on this switch; it exists so tests can compare both kernels.  Default: on.
+ * A request for the static-flow image (opt_static_flow) always takes the exact kernel. */
+int mod_set_static_flow_filter(mod_ctx* ctx, int enabled);
+/* Number of pixels the filter could not decide since the last reset (synchronises the device). */
+int mod_filter_fallbacks(mod_ctx* ctx, int reset, unsigned long long* count);
+
 /* ---- host batched streaming path (end-to-end: H2D + kernels + D2H inside the call) --------------------------- */
 /* A sequence of n_frames disparity images (host, dense, preferably pinned) forms n_frames-1 frame pairs:
  * pair i = (prev = frame i, now = frame i+1), flows[i] and transforms[i]/dt[i] belong to pair i.

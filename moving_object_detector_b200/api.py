@@ -151,6 +151,16 @@ class Context:
         """The context's own cudaStream_t as an integer handle."""
         return int(self._lib.mod_stream(self._h) or 0)
 
+    def set_static_flow_filter(self, enabled: bool) -> None:
+        """Switches the filtered residual gate of the scene-flow kernel (outputs are identical either way)."""
+        self._check(self._lib.mod_set_static_flow_filter(self._h, 1 if enabled else 0))
+
+    def filter_fallbacks(self, reset: bool = True) -> int:
+        """Pixels the filter left undecided (re-evaluated exactly) since the last reset."""
+        n = C.c_ulonglong(0)
+        self._check(self._lib.mod_filter_fallbacks(self._h, 1 if reset else 0, C.byref(n)))
+        return int(n.value)
+
     def selfcheck_ddiv(self, a, b, stream: int = 0) -> int:
         """a, b: float64 CUDA tensors.  Returns the number of pairs where the kernel's division differs from IEEE."""
         import torch

@@ -51,8 +51,12 @@ struct mod_ctx {
 
   // ray look-up tables (projectPixelTo3dRay), cached per camera / size
   double* d_ray = nullptr;
+  float* d_rayf = nullptr;   // float roundings of the tables (static-flow filter), same layout
+  unsigned long long* d_filter_fallbacks = nullptr;
+  bool static_flow_filter = true;  // mod_set_static_flow_filter
   mod_camera lut_cam{};
   int lut_w = 0, lut_h = 0;
+  int lut_stride = 0;        // offset of the row table inside d_ray / d_rayf
 
   // clusterer workspaces (max_batch frames)
   int* d_parent = nullptr;
@@ -163,11 +167,64 @@ float safe_disparity(const SfPair& p, double ray_x_max, double ray_y_max) {
   return mod::float_ceil_of_double(d);
 }
 
+// ---- static-flow filter constants (sceneflow.cu, "filtered residual gate") ----------------------------------------
+// A constant is usable by the float evaluation if it is finite and either 0 or of moderate magnitude, so that its
+// float rounding has relative error <= 2^-24 and no product of the bounded operands can overflow or go subnormal.
+bool filter_const_ok(double c, double lo = 9.094947017729282e-13 /* 2^-40 */, double hi = 1099511627776.0 /* 2^40 */) {
+  if (!std::isfinite(c)) return false;
+  const double a = std::fabs(c);
+  return a == 0.0 || (a >= lo && a <= hi);
+}
+
+float float_up(double v) { return mod::float_ceil_of_double(v * (1.0 + 1e-6)); }
+
+// Camera-level constants; returns false when the filter must stay off for this camera / size.
+bool fill_filter_camera(SfLaunch& L, const mod_camera& cam, int w, int h) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  const double lo_f = 9.765625e-4 /* 2^-10 */, hi_f = 1073741824.0 /* 2^30 */;
+  const bool ok = filter_const_ok(cam.fx, lo_f, hi_f) && cam.fx != 0.0 && filter_const_ok(cam.fy, lo_f, hi_f) &&
+                  cam.fy != 0.0 && filter_const_ok(cam.cx) && filter_const_ok(cam.cy) && filter_const_ok(cam.Tx) &&
+                  filter_const_ok(cam.Ty) && std::fabs(cam.cx) <= 1073741824.0 && std::fabs(cam.cy) <= 1073741824.0 &&
+                  w <= (1 << 20) && h <= (1 << 20);
+  L.fxf = static_cast<float>(cam.fx);
+  L.fyf = static_cast<float>(cam.fy);
+  L.cxf = static_cast<float>(cam.cx);
+  L.cyf = static_cast<float>(cam.cy);
+  L.Txf = static_cast<float>(cam.Tx);
+  L.Tyf = static_cast<float>(cam.Ty);
+  const double phi = std::fmax(std::fabs(cam.fx), std::fabs(cam.fy));
+  const double Tm = std::fmax(std::fabs(cam.Tx), std::fabs(cam.Ty));
+  L.aN = float_up(41.0 * u * phi);
+  L.bN = float_up(2.1 * (phi * 1.01 * 8.673617379884035e-19 /* 2^-60 */ + 2.0 * u * Tm) + 8.673617379884035e-19);
+  L.Cw = float_up(std::fabs(cam.cx) + std::fabs(cam.cy) + w + h);
+  return ok;
+}
+
+// Pair-level constants; rho = +inf switches the filter off for the pair (every pixel is then evaluated exactly).
+void fill_filter_pair(SfPair& p, bool camera_ok) {
+  bool ok = camera_ok && filter_const_ok(static_cast<double>(p.fT_prev)) && p.fT_prev != 0.0f &&
+            std::isfinite(p.min_prev) && std::isfinite(p.max_prev) && std::fabs(p.min_prev) <= 1099511627776.0f &&
+            std::fabs(p.max_prev) <= 1099511627776.0f;
+  double rho = 0.0, tau = 0.0;
+  for (int k = 0; k < 9; k++) {
+    ok = ok && filter_const_ok(p.R[k]);
+    p.Rf[k] = static_cast<float>(p.R[k]);
+    rho = std::fmax(rho, std::fabs(p.R[k]));
+  }
+  for (int k = 0; k < 3; k++) {
+    ok = ok && filter_const_ok(p.t[k]);
+    p.tf[k] = static_cast<float>(p.t[k]);
+    tau = std::fmax(tau, std::fabs(p.t[k]));
+  }
+  p.rho = ok ? float_up(rho) : INFINITY;
+  p.tau = ok ? float_up(tau) : INFINITY;
+}
+
 bool same_camera(const mod_camera& a, const mod_camera& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
 
 int ensure_lut(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_camera& cam) {
   if (ctx->lut_w == w && ctx->lut_h == h && same_camera(ctx->lut_cam, cam)) return MOD_OK;
-  launch_ray_lut(s, ctx->d_ray, ctx->d_ray + ctx->max_w, w, h, cam);
+  launch_ray_lut(s, ctx->d_ray, ctx->d_ray + ctx->lut_stride, ctx->d_rayf, ctx->d_rayf + ctx->lut_stride, w, h, cam);
   MOD_CK(ctx, cudaGetLastError());
   ctx->launches++;
   ctx->lut_cam = cam;
@@ -194,7 +251,7 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
   SfLaunch L;
   std::memset(&L, 0, sizeof(L));
   L.ray_x = ctx->d_ray;
-  L.ray_y = ctx->d_ray + ctx->max_w;
+  L.ray_y = ctx->d_ray + ctx->lut_stride;
   L.fx = cam.fx;
   L.fy = cam.fy;
   L.cx = cam.cx;
@@ -216,6 +273,11 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
   L.mask = d_mask;
   L.depth = d_depth;
   L.static_flow = d_static;
+  L.ray_xf = ctx->d_rayf;
+  L.ray_yf = ctx->d_rayf + ctx->lut_stride;
+  const bool camera_ok = fill_filter_camera(L, cam, w, h);
+  L.use_filter = ctx->static_flow_filter ? 1 : 0;
+  L.filter_fallbacks = ctx->d_filter_fallbacks;
   for (int first = 0; first < batch; first += kSfMaxPairsPerLaunch) {
     const int n = (batch - first < kSfMaxPairsPerLaunch) ? batch - first : kSfMaxPairsPerLaunch;
     for (int k = 0; k < n; k++) {
@@ -233,6 +295,7 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
       p.min_prev = src.min_disparity_prev;
       p.max_prev = src.max_disparity_prev;
       p.d_safe = safe_disparity(p, ray_x_max, ray_y_max);
+      fill_filter_pair(p, camera_ok);
       p.pad = 0.0f;
     }
     L.first_frame = first;
@@ -403,6 +466,21 @@ int mod_selfcheck_ddiv(mod_ctx* ctx, void* stream, const double* d_a, const doub
   return MOD_OK;
 }
 
+int mod_set_static_flow_filter(mod_ctx* ctx, int enabled) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  ctx->static_flow_filter = enabled != 0;
+  return MOD_OK;
+}
+
+int mod_filter_fallbacks(mod_ctx* ctx, int reset, unsigned long long* count) {
+  if (!ctx || !count) return MOD_ERR_INVALID_ARG;
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  MOD_CK(ctx, cudaDeviceSynchronize());
+  MOD_CK(ctx, cudaMemcpy(count, ctx->d_filter_fallbacks, sizeof(*count), cudaMemcpyDeviceToHost));
+  if (reset) MOD_CK(ctx, cudaMemset(ctx->d_filter_fallbacks, 0, sizeof(*count)));
+  return MOD_OK;
+}
+
 void* mod_stream(const mod_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {
@@ -433,7 +511,12 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ok(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
   ok(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-  ok(dev_alloc(&ctx->d_ray, static_cast<size_t>(max_w) + max_h));
+  // the row table starts at max_w rounded up to even so that the second table of each pair stays 16 / 8-byte aligned
+  ctx->lut_stride = max_w + (max_w & 1);
+  ok(dev_alloc(&ctx->d_ray, static_cast<size_t>(ctx->lut_stride) + max_h));
+  ok(dev_alloc(&ctx->d_rayf, static_cast<size_t>(ctx->lut_stride) + max_h));
+  ok(dev_alloc(&ctx->d_filter_fallbacks, 1));
+  if (e == cudaSuccess) ok(cudaMemset(ctx->d_filter_fallbacks, 0, sizeof(unsigned long long)));
   ok(dev_alloc(&ctx->d_parent, N));
   ok(dev_alloc(&ctx->d_count, N));
   ok(dev_alloc(&ctx->d_tstat, N));
@@ -461,6 +544,8 @@ void mod_destroy(mod_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->d_ray);
+  cudaFree(ctx->d_rayf);
+  cudaFree(ctx->d_filter_fallbacks);
   cudaFree(ctx->d_parent);
   cudaFree(ctx->d_count);
   cudaFree(ctx->d_tstat);

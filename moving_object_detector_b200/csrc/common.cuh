@@ -23,16 +23,28 @@ struct SfPair {
   float fT_now, min_now, max_now;     // f*T evaluated in float as at disparity_image_processor.cpp:43
   float fT_prev, min_prev, max_prev;
   float d_safe;            // previous disparities >= d_safe are known to ego-transform to a finite, non-NaN x
+  // float copies for the static-flow filter (sceneflow.cu, "filtered residual gate"); rho = +inf disables it
+  float rho;               // >= max |R_ij| (float copies)
+  float Rf[9], tf[3];
+  float tau;               // >= max |t_i|
   float pad;
 };
 
-constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 168 B = 10.5 KB of the 32 KB parameter space
+constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 224 B = 14 KB of the 32 KB parameter space
 
 struct SfLaunch {
   SfPair pair[kSfMaxPairsPerLaunch];
   const double* ray_x;  // [w]  ((double)u - cx - Tx) / fx   (PinholeCameraModel::projectPixelTo3dRay)
   const double* ray_y;  // [h]  ((double)v - cy - Ty) / fy
+  const float* ray_xf;  // float roundings of the two tables (static-flow filter)
+  const float* ray_yf;
   double fx, fy, cx, cy, Tx, Ty;
+  float fxf, fyf, cxf, cyf, Txf, Tyf;  // float roundings of the camera (static-flow filter)
+  float aN, bN;          // error of the projected numerator: dN' = aN * S + bN
+  float Cw;              // >= |cx| + |cy| + w + h
+  int prefetch_rows;     // rows ahead whose inputs each thread pulls into L2 (set by launch_scene_flow; 0 = off)
+  int use_filter;        // 0: evaluate the static flow exactly for every pixel
+  unsigned long long* filter_fallbacks;  // pixels the filter could not decide (re-evaluated exactly); may be null
   int w, h;
   float flow_thr2;       // sqrtf(s) >= (float)dynamic_flow_diff  <=>  s >= flow_thr2   (sq_threshold)
   float speed_thr2;      // (double)sqrtf(s) >= dynamic_speed     <=>  s >= speed_thr2
@@ -89,7 +101,8 @@ struct ClusterStat {
   int pad;
 };
 
-void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, int w, int h, const mod_camera& cam);
+void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, float* d_ray_xf, float* d_ray_yf, int w, int h,
+                    const mod_camera& cam);
 cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs);
 cudaError_t launch_ddiv_check(cudaStream_t s, const double* a, const double* b, size_t n, unsigned long long* n_bad);
 cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame_stride_points, uint8_t* mask, int w,

@@ -1,12 +1,12 @@
 #!/bin/bash
-# usage: run_variants.sh out.log  -- benchmarks every scratch/variants/*.so (scene-flow kernel time from bench.py)
-out=$1
+# usage: run_variants.sh out.log [env assignments...] -- benchmarks every scratch/variants/*.so (scene-flow kernel time from bench.py)
+out=$1; shift
 : > $out
 for so in /root/repo/scratch/variants/*.so; do
   n=$(basename $so .so)
-  MOD_B200_LIB=$so python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+  env "$@" MOD_B200_LIB=$so python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 l=json.loads(sys.stdin.readline()); r=l['roofline']
-print('$n', 'sf_ms=%.4f frac=%.3f step_ms=%.3f value=%.0f' % (r['kernel_ms'], r['frac'], l['ms_per_step'], l['value']))" >> $out 2>&1
+print('$n $*', 'sf_ms=%.4f frac=%.3f step_ms=%.3f value=%.0f' % (r['kernel_ms'], r['frac'], l['ms_per_step'], l['value']))" >> $out 2>&1
 done
 cat $out

@@ -90,14 +90,18 @@ def test_cluster_long_root_chains_are_repeatable(oracle):
 
 @pytest.mark.parametrize("w,h", [(100, 37), (98, 41), (97, 33), (64, 8), (68, 9), (2, 2), (1, 5), (260, 16)])
 def test_scene_flow_every_kernel_path_and_ragged_sizes(oracle, w, h):
-    """w % 4 == 0 takes the TMA-staged persistent kernel (partial tiles on both edges), other even widths the
-    two-pixel direct kernel, odd widths the one-pixel kernel; all must equal the oracle bit for bit."""
+    """Even widths take the two-pixel-per-thread kernel (partial tiles on both edges), odd widths the one-pixel
+    kernel; with the static-flow image requested the exact kernel runs, without it the filtered one.  All must equal
+    the oracle bit for bit (the prefetch of rows below the image / beyond the batch must stay in bounds)."""
     cfg = dataclasses.replace(synth.CONFIGS["gazebo_640x480"], w=w, h=h, fx=80.0, cx=w / 2 + 0.5, cy=h / 2 + 0.5,
                               seed=9000 + w, n_invalid_rects=1, n_movers=1)
     seq = synth.make_sequence(cfg, 2)
     with Context(max(w, 8), max(h, 8), max_batch=1) as c:
         got, depth, static = c.scene_flow(**seq_inputs(seq, 0), want_depth=True, want_static_flow=True)
+        got_f, depth_f, _ = c.scene_flow(**seq_inputs(seq, 0), want_depth=True)
     want = oracle_scene_flow(oracle, seq, 0, want_depth=True, want_static=True)
     assert_cloud_bit_exact(got, want["points32"], "cloud")
+    assert_cloud_bit_exact(got_f, want["points32"], "cloud (filtered kernel)")
+    assert_cloud_bit_exact(depth_f[..., None], want["depth"][..., None], "depth (filtered kernel)")
     assert_cloud_bit_exact(depth[..., None], want["depth"][..., None], "depth")
     assert_cloud_bit_exact(static, want["static_flow"], "static flow")
