@@ -63,6 +63,7 @@ struct mod_ctx {
   int* d_count = nullptr;
   TileStat* d_tstat = nullptr;
   uint32_t* d_list = nullptr;
+  uint32_t* d_list_speed = nullptr;
   uint32_t* d_border_mask = nullptr;
   uint32_t* d_member_speed = nullptr;
   int* d_member_pixel = nullptr;
@@ -353,6 +354,7 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   X.work_count = ctx->d_work;
   X.work_cursor = ctx->d_work + 1;
   X.list = ctx->d_list;
+  X.list_speed = ctx->d_list_speed;
   X.border_mask = ctx->d_border_mask;
   X.work_items = ctx->d_work_items;
   X.member_offset = ctx->d_member_offset;
@@ -521,6 +523,7 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   ok(dev_alloc(&ctx->d_count, N));
   ok(dev_alloc(&ctx->d_tstat, N));
   ok(dev_alloc(&ctx->d_list, N));
+  ok(dev_alloc(&ctx->d_list_speed, N));
   ok(dev_alloc(&ctx->d_border_mask, N));
   ok(dev_alloc(&ctx->d_member_speed, N));
   ok(dev_alloc(&ctx->d_member_pixel, N));
@@ -550,6 +553,7 @@ void mod_destroy(mod_ctx* ctx) {
   cudaFree(ctx->d_count);
   cudaFree(ctx->d_tstat);
   cudaFree(ctx->d_list);
+  cudaFree(ctx->d_list_speed);
   cudaFree(ctx->d_border_mask);
   cudaFree(ctx->d_member_speed);
   cudaFree(ctx->d_member_pixel);

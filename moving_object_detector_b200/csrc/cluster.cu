@@ -257,7 +257,8 @@ constexpr uint8_t kUp = 4;    // edge to the upper neighbour accepted
 // NC == 0 is the generic path for N in 5..10 (runtime N, window_edges).
 template <int NC>
 __global__ void __launch_bounds__(kBlock)
-    cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ border_list,
+    cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
+                   uint32_t* __restrict__ border_list,
                    uint32_t* __restrict__ border_mask, uint32_t* __restrict__ root_list,
                    int* __restrict__ counters /* list, border, root */) {
   constexpr int kMaxN = 10;
@@ -521,6 +522,11 @@ __global__ void __launch_bounds__(kBlock)
       L.parent[fb + i] = (ty0 + (r >> 5)) * L.w + tx0 + (r & 31);
       list[s_base + e] = static_cast<uint32_t>(fb + i);
       const float4 xyz = __ldg(reinterpret_cast<const float4*>(pts + static_cast<size_t>(i) * 8));
+      // |v| (Vector3f::norm, the oracle's summation order) rides along with the list entry: the record's second half
+      // sits in the same 32-byte sector, and cl_scatter then reads 4 bytes per member instead of a sector
+      const float4 vel = __ldg(reinterpret_cast<const float4*>(pts + static_cast<size_t>(i) * 8 + 4));
+      list_speed[s_base + e] = __float_as_uint(__fsqrt_rn(
+          __fadd_rn(__fadd_rn(__fmul_rn(vel.x, vel.x), __fmul_rn(vel.y, vel.y)), __fmul_rn(vel.z, vel.z))));
       const float cc[3] = {xyz.x, xyz.y, xyz.z};
 #pragma unroll
       for (int k = 0; k < 3; k++)  // NaN coordinates are skipped (order dependent in the reference; unpinned)
@@ -610,12 +616,32 @@ __global__ void __launch_bounds__(kBlock)
       }
     }
     const int lx = u & (kTileW - 1), ly = v & (kTileH - 1);
-    while (__any_sync(kFull, !edges.empty())) {
-      if (!edges.empty()) {
+    // Every pixel's parent entry holds its tile root (cl_tile) or, after path halving, an ancestor of it; all border
+    // pixels along one tile edge share a handful of (root, root) pairs and consecutive list entries come from the
+    // same tile, so the pairs are de-duplicated inside the warp first: one lane per distinct pair performs the
+    // union.  Without this, thousands of finds per blob converge on the same parent entry (one L2 slice): measured
+    // 98 -> 60 us per 63 720p frames.
+    int ra = -1;
+    if (t < n) ra = __ldcg(parent + i);
+    const uint32_t fbase = static_cast<uint32_t>(parent - L.parent);
+    for (;;) {
+      const bool has = !edges.empty();
+      if (__ballot_sync(kFull, has) == 0) break;
+      bool cross = false;
+      int rb = -1;
+      if (has) {
         const int k = edges.pop();
         const int wy = k / stride, wx = k - wy * stride;
         const int dx = wx - N, dy = wy - N;
-        if (NC > 0 || lx + dx < 0 || ly + dy < 0) uf_union(parent, i, (v + dy) * L.w + (u + dx));  // other tile
+        cross = NC > 0 || lx + dx < 0 || ly + dy < 0;  // the up-left endpoint lies in another tile
+        if (cross) rb = __ldcg(parent + (v + dy) * L.w + (u + dx));
+      }
+      const unsigned crossing = __ballot_sync(kFull, cross);
+      if (cross) {
+        const unsigned long long key =
+            (static_cast<unsigned long long>(fbase + static_cast<uint32_t>(ra)) << 32) | static_cast<uint32_t>(rb);
+        const unsigned same = __match_any_sync(crossing, key);
+        if ((threadIdx.x & 31) == __ffs(same) - 1 && ra != rb) uf_union(parent, ra, rb);
       }
       __syncwarp();
     }
@@ -750,7 +776,8 @@ __global__ void __launch_bounds__(kBlock)
 // irrelevant to every consumer: min/max, k-th largest speed).  |v| is evaluated here, as Vector3f::norm() with the
 // oracle's summation order.
 __global__ void __launch_bounds__(kBlock)
-    cl_scatter_kernel(const ClLaunch L, const uint32_t* __restrict__ list, const int* __restrict__ list_count,
+    cl_scatter_kernel(const ClLaunch L, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_speed,
+                      const int* __restrict__ list_count,
                       const int* __restrict__ member_offset, int* __restrict__ cursor,
                       uint32_t* __restrict__ member_speed, int* __restrict__ member_pixel) {
   const int n = *list_count;
@@ -779,11 +806,7 @@ __global__ void __launch_bounds__(kBlock)
       if (lane == leader) base = atomicAdd(cursor + cs, __popc(same));
       base = __shfl_sync(same, base, leader);
       const size_t pos = static_cast<size_t>(frame) * P + member_offset[cs] + base + __popc(same & ((1u << lane) - 1));
-      const float4 vel = __ldg(reinterpret_cast<const float4*>(
-          L.points + (static_cast<size_t>(frame) * L.points_frame_stride + i) * 8 + 4));
-      const float speed = __fsqrt_rn(
-          __fadd_rn(__fadd_rn(__fmul_rn(vel.x, vel.x), __fmul_rn(vel.y, vel.y)), __fmul_rn(vel.z, vel.z)));
-      member_speed[pos] = __float_as_uint(speed);  // speeds are >= 0: the bit pattern is monotone
+      member_speed[pos] = list_speed[t];  // |v| from cl_tile; speeds are >= 0: the bit pattern is monotone
       member_pixel[pos] = i;
     }
   }
@@ -801,7 +824,7 @@ constexpr int kObjBlock = 1024;
 constexpr int kSmemMembers = 9216;  // 36 KB
 constexpr int kBins = 2048;
 
-__global__ void __launch_bounds__(kObjBlock)
+__global__ void __launch_bounds__(kObjBlock, 2)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
                       int* __restrict__ work_cursor, const int* __restrict__ member_offset,
                       const uint32_t* __restrict__ member_speed, const int* __restrict__ member_pixel) {
@@ -858,8 +881,15 @@ __global__ void __launch_bounds__(kObjBlock)
         for (int q = 0; q < 4; q++) {
           int bin = -1;
           if (ok[q] && (v[q] & himask) == prefix) bin = static_cast<int>((v[q] >> shift) & binmask);
-          const unsigned same = __match_any_sync(kFull, bin);
-          if (bin >= 0 && lane == __ffs(same) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(same)));
+          // members of one object move alike: in the first pass nearly every warp is uniform (one atomic per warp);
+          // later passes spread over the bins and plain shared-memory atomics are cheaper than a match
+          int uniform;
+          __match_all_sync(kFull, bin, &uniform);
+          if (uniform) {
+            if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
+          } else if (bin >= 0) {
+            atomicAdd(&hist[bin], 1u);
+          }
         }
       }
       __syncthreads();
@@ -958,7 +988,7 @@ template <int NC>
 void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint32_t* border_list, uint32_t* root_list,
                        int* counters) {
   const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
-  cl_tile_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, border_list, X.border_mask, root_list, counters);
+  cl_tile_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list, counters);
   cl_merge_kernel<NC><<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
 }
 
@@ -991,9 +1021,9 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
   cl_slots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
   cl_rank_kernel<<<L.batch, kBlock, static_cast<size_t>(L.max_clusters) * sizeof(int), s>>>(L, X.work_count, X.work_items,
                                                                                           X.member_offset);
-  cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, counters, X.member_offset, X.cursor, X.member_speed,
+  cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, X.list_speed, counters, X.member_offset, X.cursor, X.member_speed,
                                                  X.member_pixel);
-  cl_objects_kernel<<<148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
+  cl_objects_kernel<<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
                                               X.member_speed, X.member_pixel);
   if (L.labels != nullptr) {
     size_t lb = (total + kBlock - 1) / kBlock;

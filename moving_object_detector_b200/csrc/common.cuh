@@ -112,6 +112,7 @@ struct ClExtra {
   int* work_count;         // [5]   work_count, work_cursor, list_count, border_count, root_count (one reset)
   int* work_cursor;        // = work_count + 1
   uint32_t* list;          // [batch * w*h]  compacted global indices (frame*P + i) of the dynamic pixels
+  uint32_t* list_speed;    // [batch * w*h]  |v| bits of the same entries
   uint32_t* border_mask;   // [batch * w*h]  per border-list entry: window cells of its cross-tile edges (N <= 4)
   int2* work_items;        // [batch * max_clusters]  (frame, slot) of every surviving cluster
   int* member_offset;      // [batch * max_clusters]  start of the cluster's member list inside its frame

@@ -1,0 +1,270 @@
+"""GPU parity at the BASELINE.json configurations: KITTI-scale batch, HD2K clusterer stress at
+neighbor_distance 1 / 4 / 10, a 4K frame, the 720p sequence through the host streaming call; plus the edge cases of
+the boundary (empty and saturated frames, capacity and parameter errors) and size-independent properties of the
+full-size device-resident batch the benchmark times."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from helpers import assert_cloud_bit_exact, assert_objects_match, oracle_scene_flow, seq_inputs
+from moving_object_detector_b200 import (CameraInfo, ClustererConfig, Context, ModError, SceneFlowConstructorConfig,
+                                         TransformMsg, synth)
+from moving_object_detector_b200.api import OBJECT_DTYPE, STATS_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+MAX_OBJS = 64
+
+
+def _run_batched(seq, cfg, B, cl_cfg, want_labels=True):
+    """scene flow + clusterer over B device-resident pairs (the bench path); returns numpy outputs."""
+    import torch
+    dev = "cuda:0"
+    W, H = cfg.w, cfg.h
+    disp = torch.as_tensor(np.asarray(seq["disp"])).to(dev)
+    flows = torch.as_tensor(np.asarray(seq["flows"])).to(dev)
+    cam = CameraInfo.pinhole(*seq["cam"])
+    transforms = [TransformMsg(t[:3], t[3:]) for t in seq["transforms"]]
+    with Context(W, H, max_batch=B) as c:
+        pairs = Context.make_pairs([disp[i + 1] for i in range(B)], [disp[i] for i in range(B)],
+                                   [flows[i] for i in range(B)], transforms, seq["dts"], seq["f"], seq["T"],
+                                   seq["min_disparity"], seq["max_disparity"])
+        pts = torch.empty((B, H * W, 8), dtype=torch.float32, device=dev)
+        msk = torch.empty((B, H * W), dtype=torch.uint8, device=dev)
+        lab = torch.empty((B, H * W), dtype=torch.int32, device=dev) if want_labels else None
+        objs = torch.zeros((B, MAX_OBJS * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        c.scene_flow_batched_dev(W, H, pairs, cam, SceneFlowConstructorConfig(), cl_cfg.dynamic_speed, pts, msk,
+                                 stream=stream)
+        c.cluster_batched_dev(W, H, B, pts, msk, cl_cfg, objs, stats, MAX_OBJS, labels=lab, stream=stream)
+        torch.cuda.synchronize()
+        out = dict(points=pts.cpu().numpy().reshape(B, H, W, 8), mask=msk.cpu().numpy().reshape(B, H, W),
+                   labels=lab.cpu().numpy().reshape(B, H, W) if want_labels else None,
+                   objs=objs.cpu().numpy().view(OBJECT_DTYPE).reshape(B, MAX_OBJS),
+                   stats=stats.cpu().numpy().view(STATS_DTYPE).reshape(B))
+    return out
+
+
+def _check_batch_against_oracle(oracle, seq, out, B, cl_cfg):
+    for i in range(B):
+        want = oracle_scene_flow(oracle, seq, i)
+        assert_cloud_bit_exact(out["points"][i], want["points32"], f"pair {i} cloud")
+        wc = oracle.cluster(want["points32"], cl_cfg.cluster_size, cl_cfg.depth_diff, cl_cfg.dynamic_speed,
+                            cl_cfg.neighbor_distance)
+        assert np.array_equal(out["labels"][i], wc["labels"]), f"pair {i} labels"
+        n = int(out["stats"][i]["n_objects"])
+        assert n == wc["n_objects"] and out["stats"][i]["status"] == 0
+        assert_objects_match(out["objs"][i][:n], wc["objects"], want["points32"], wc["labels"])
+        v = want["points32"][..., 4:7]
+        speed = np.sqrt((v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2])
+        assert np.array_equal(out["mask"][i] != 0, speed.astype(np.float64) >= cl_cfg.dynamic_speed), f"pair {i} mask"
+        assert int(out["stats"][i]["n_dynamic"]) == int((out["mask"][i] != 0).sum())
+
+
+def test_kitti_scale_batch_matches_oracle(oracle):
+    """config 3: 1242x375 (even width, not a multiple of 4 or 32: partial tiles in both kernels)."""
+    cfg = synth.CONFIGS["kitti_1242x375"]
+    B = 4
+    seq = synth.make_sequence(cfg, B + 1)
+    cl = ClustererConfig(cluster_size=400)
+    out = _run_batched(seq, cfg, B, cl)
+    _check_batch_against_oracle(oracle, seq, out, B, cl)
+    assert out["stats"]["n_objects"].sum() > 0
+
+
+def test_zed_720p_batch_matches_oracle(oracle):
+    """config 2, the benchmark workload, through the device-resident batched calls the benchmark times."""
+    cfg = synth.CONFIGS["zed_1280x720"]
+    B = 3
+    seq = synth.make_sequence(cfg, B + 1)
+    cl = ClustererConfig()
+    out = _run_batched(seq, cfg, B, cl)
+    _check_batch_against_oracle(oracle, seq, out, B, cl)
+    assert out["stats"]["n_objects"].min() >= 2
+
+
+def test_uhd_frame_matches_oracle(oracle):
+    """config 5: one 3840x2160 pair."""
+    cfg = synth.CONFIGS["uhd_3840x2160"]
+    seq = synth.make_sequence(cfg, 2)
+    cl = ClustererConfig()
+    out = _run_batched(seq, cfg, 1, cl)
+    _check_batch_against_oracle(oracle, seq, out, 1, cl)
+
+
+@pytest.mark.parametrize("n", [1, 4, 10])
+def test_hd2k_clusterer_stress_matches_oracle(oracle, n):
+    """config 4: 2208x1242 with ~45 % dynamic pixels -- serpentine, blobs straddling cluster_size, specks,
+    checkerboards, depth steps -- at neighbor_distance 1 (fast path), 4 (default), 10 (generic path)."""
+    cloud, dyn = synth.make_stress_cloud(2208, 1242)
+    cfg = ClustererConfig(cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=n)
+    want = oracle.cluster(cloud, 2500, 0.15, 0.3, n)
+    with Context(2208, 1242, max_batch=1) as c:
+        got = c.cluster(cloud, cfg, max_objs=1024)
+    assert want["n_objects"] > 20
+    assert np.array_equal(got.labels, want["labels"])
+    assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
+
+
+def test_sequence_host_streaming_matches_oracle(oracle):
+    """mod_pipeline_sequence_host (the e2e benchmark call): host frames in, objects + clouds out, chunked uploads."""
+    cfg = dataclasses.replace(synth.CONFIGS["zed_1280x720"], seed=2102)
+    n_pairs = 5
+    seq = synth.make_sequence(cfg, n_pairs + 1)
+    disp = np.ascontiguousarray(np.asarray(seq["disp"]))
+    flows = np.ascontiguousarray(np.asarray(seq["flows"]))
+    H, W = disp.shape[1:]
+    objs = np.zeros((n_pairs, MAX_OBJS), OBJECT_DTYPE)
+    stats = np.zeros(n_pairs, STATS_DTYPE)
+    cloud = np.empty((n_pairs, H, W, 8), np.float32)
+    with Context(W, H, max_batch=4) as c:  # max_batch < n_pairs: the call must chunk
+        c.pipeline_sequence_host(disp, flows, CameraInfo.pinhole(*seq["cam"]),
+                                 [TransformMsg(t[:3], t[3:]) for t in seq["transforms"]], seq["dts"], seq["f"],
+                                 seq["T"], seq["min_disparity"], seq["max_disparity"], SceneFlowConstructorConfig(),
+                                 ClustererConfig(), objs, stats, MAX_OBJS, out_points32=cloud)
+    for i in range(n_pairs):
+        want = oracle_scene_flow(oracle, seq, i)
+        assert_cloud_bit_exact(cloud[i], want["points32"], f"pair {i}")
+        wc = oracle.cluster(want["points32"])
+        n = int(stats[i]["n_objects"])
+        assert n == wc["n_objects"] and stats[i]["status"] == 0
+        assert_objects_match(objs[i][:n], wc["objects"], want["points32"], wc["labels"])
+
+
+# ---- edge cases of the boundary -------------------------------------------------------------------------------------
+
+def _tiny_seq(**kw):
+    cfg = dataclasses.replace(synth.CONFIGS["gazebo_640x480"], w=192, h=128, fx=170.0, cx=96.5, cy=64.5, seed=777,
+                              n_invalid_rects=1, **kw)
+    return cfg, dict(synth.make_sequence(cfg, 2))
+
+
+def test_static_scene_gives_no_objects(oracle):
+    cfg, seq = _tiny_seq(n_movers=0)
+    with Context(192, 128) as c:
+        res = c.pipeline(**seq_inputs(seq, 0), want_points=True)
+    want = oracle_scene_flow(oracle, seq, 0)
+    assert_cloud_bit_exact(res.points32, want["points32"])
+    assert res.n_objects == 0 and (res.labels == -1).all()
+
+
+@pytest.mark.parametrize("fill", [float("nan"), 0.0, -1.0, float("inf"), 500.0])
+def test_all_invalid_disparity_gives_nan_cloud(oracle, fill):
+    cfg, seq = _tiny_seq()
+    disp = np.full_like(np.asarray(seq["disp"]), fill)
+    seq["disp"] = disp
+    with Context(192, 128) as c:
+        res = c.pipeline(**seq_inputs(seq, 0), want_points=True)
+    want = oracle_scene_flow(oracle, seq, 0)
+    assert_cloud_bit_exact(res.points32, want["points32"])
+    assert np.isnan(res.points32[..., [0, 1, 2, 4, 5, 6]]).all() and res.n_objects == 0
+
+
+def test_every_pixel_dynamic_single_cluster(oracle):
+    h, w = 96, 160
+    cloud = np.zeros((h, w, 8), np.float32)
+    cloud[..., 2] = 5.0
+    cloud[..., 0] = np.linspace(-1, 1, w, dtype=np.float32)[None, :]
+    cloud[..., 1] = np.linspace(-1, 1, h, dtype=np.float32)[:, None]
+    cloud[..., 4] = 1.0
+    want = oracle.cluster(cloud, 100, 0.15, 0.3, 4)
+    with Context(w, h) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=100))
+    assert want["n_objects"] == 1 and got.n_objects == 1
+    assert np.array_equal(got.labels, want["labels"]) and (got.labels == 0).all()
+    assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
+
+
+def test_capacity_and_parameter_errors(oracle):
+    from moving_object_detector_b200 import _lib
+    cloud, _ = synth.make_stress_cloud(320, 240, seed=5, cluster_size=120)
+    want = oracle.cluster(cloud, 120, 0.15, 0.3, 4)
+    assert want["n_objects"] > 3
+    with Context(320, 240) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=120), max_objs=2)
+        assert got.status == _lib.MOD_ERR_CAPACITY and got.n_objects == want["n_objects"] and len(got.objects) == 2
+        assert_objects_match(got.objects, want["objects"][:2], cloud, want["labels"])
+        with pytest.raises(ModError) as e:
+            c.cluster(cloud, ClustererConfig(cluster_size=0))
+        assert e.value.status == _lib.MOD_ERR_INVALID_PARAM
+        with pytest.raises(ModError) as e:
+            c.cluster(cloud, ClustererConfig(neighbor_distance=-1))
+        assert e.value.status == _lib.MOD_ERR_INVALID_PARAM
+        # a negative cluster_size removes everything (size_t comparison, clusterer_nodelet.cpp:374)
+        got = c.cluster(cloud, ClustererConfig(cluster_size=-1))
+        assert got.n_objects == 0 and (got.labels == -1).all()
+        # the context still works after the errors
+        got = c.cluster(cloud, ClustererConfig(cluster_size=120), max_objs=256)
+        assert np.array_equal(got.labels, want["labels"])
+    with pytest.raises(ModError):
+        with Context(64, 64) as c:
+            c.cluster(cloud, ClustererConfig())  # frame larger than the context
+
+
+def test_neighbor_distance_zero_labels_nothing(oracle):
+    cloud, _ = synth.make_stress_cloud(320, 240, seed=6, cluster_size=50)
+    want = oracle.cluster(cloud, 50, 0.15, 0.3, 0)
+    with Context(320, 240) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=50, neighbor_distance=0))
+    assert want["n_objects"] == 0 and got.n_objects == 0
+    assert np.array_equal(got.labels, want["labels"])
+
+
+# ---- size-independent properties at the benchmark's full batch --------------------------------------------------------
+
+def test_full_batch_properties():
+    """63 pairs of 1280x720 (BASELINE.json's metric configuration): repeatable bit for bit; the mask equals
+    |v| >= dynamic_speed recomputed from the cloud; label histogram, object sizes and n_dynamic agree; every
+    surviving cluster is >= cluster_size; ids are dense."""
+    import torch
+    cfg = synth.CONFIGS["zed_1280x720"]
+    B = 63
+    dev = "cuda:0"
+    seq = synth.make_sequence(cfg, B + 1, device=dev)
+    W, H = cfg.w, cfg.h
+    disp, flows = seq["disp"], seq["flows"]
+    cam = CameraInfo.pinhole(*seq["cam"])
+    transforms = [TransformMsg(t[:3], t[3:]) for t in seq["transforms"]]
+    cl = ClustererConfig()
+    results = []
+    with Context(W, H, max_batch=B) as c:
+        pairs = Context.make_pairs([disp[i + 1] for i in range(B)], [disp[i] for i in range(B)],
+                                   [flows[i] for i in range(B)], transforms, seq["dts"], seq["f"], seq["T"],
+                                   seq["min_disparity"], seq["max_disparity"])
+        stream = torch.cuda.current_stream().cuda_stream
+        for rep in range(2):
+            pts = torch.empty((B, H * W, 8), dtype=torch.float32, device=dev)
+            msk = torch.empty((B, H * W), dtype=torch.uint8, device=dev)
+            lab = torch.empty((B, H * W), dtype=torch.int32, device=dev)
+            objs = torch.zeros((B, MAX_OBJS * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+            stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+            c.scene_flow_batched_dev(W, H, pairs, cam, SceneFlowConstructorConfig(), cl.dynamic_speed, pts, msk,
+                                     stream=stream)
+            c.cluster_batched_dev(W, H, B, pts, msk, cl, objs, stats, MAX_OBJS, labels=lab, stream=stream)
+            torch.cuda.synchronize()
+            results.append((pts, msk, lab, objs, stats))
+    (p0, m0, l0, o0, s0), (p1, m1, l1, o1, s1) = results
+    assert torch.equal(p0.view(torch.int32), p1.view(torch.int32)) and torch.equal(m0, m1) and torch.equal(l0, l1)
+    assert torch.equal(s0, s1)
+    v = p0[..., 4:7]
+    speed = torch.sqrt((v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2])
+    assert torch.equal(m0 != 0, speed.double() >= cl.dynamic_speed)
+    assert not bool(((l0 >= 0) & (m0 == 0)).any()), "labelled pixels must be dynamic"
+    stats = s0.cpu().numpy().view(STATS_DTYPE).reshape(B)
+    objs = o0.cpu().numpy().view(OBJECT_DTYPE).reshape(B, MAX_OBJS)
+    objs1 = o1.cpu().numpy().view(OBJECT_DTYPE).reshape(B, MAX_OBJS)
+    labels = l0.cpu().numpy()
+    n_dyn = (m0 != 0).sum(dim=1).cpu().numpy()
+    assert (stats["status"] == 0).all() and np.array_equal(stats["n_dynamic"], n_dyn)
+    assert stats["n_objects"].sum() > 2 * B
+    for i in range(B):
+        n = int(stats[i]["n_objects"])
+        hist = np.bincount(labels[i][labels[i] >= 0], minlength=n)
+        assert len(hist) == n, "ids must be dense 0..n-1"
+        assert np.array_equal(objs[i][:n]["id"], np.arange(n))
+        assert np.array_equal(objs[i][:n]["n_points"], hist) and (hist >= cl.cluster_size).all()
+        # everything but the (tie-dependent) velocity pick must repeat exactly
+        for f in ("id", "n_points", "center", "bbox"):
+            assert np.array_equal(objs[i][:n][f], objs1[i][:n][f])
