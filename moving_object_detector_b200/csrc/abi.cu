@@ -155,8 +155,8 @@ void fill_transform(const mod_transform& m, SfPair& p) {
 // chosen so that |R0 . (rx z, ry z, z) + t0| stays far below FLT_MAX with every intermediate finite.  Anything the
 // bound cannot cover (non-finite or negative f*T, non-finite transform or camera) yields +inf: the kernel then
 // evaluates the point for every pixel that reaches the gate.
-float safe_disparity(const SfPair& p, double ray_x_max, double ray_y_max) {
-  const double fT = static_cast<double>(p.fT_prev);
+float safe_disparity(const SfPair& p, float fT_prev, double ray_x_max, double ray_y_max) {
+  const double fT = static_cast<double>(fT_prev);
   const double s = std::fabs(p.R[0]) * ray_x_max + std::fabs(p.R[1]) * ray_y_max + std::fabs(p.R[2]);
   const double t0 = std::fabs(p.t[0]);
   if (!(fT >= 0.0) || !std::isfinite(fT) || !std::isfinite(s) || !std::isfinite(t0) || !std::isfinite(ray_x_max) ||
@@ -202,23 +202,42 @@ bool fill_filter_camera(SfLaunch& L, const mod_camera& cam, int w, int h) {
 }
 
 // Pair-level constants; rho = +inf switches the filter off for the pair (every pixel is then evaluated exactly).
-void fill_filter_pair(SfPair& p, bool camera_ok) {
-  bool ok = camera_ok && filter_const_ok(static_cast<double>(p.fT_prev)) && p.fT_prev != 0.0f &&
-            std::isfinite(p.min_prev) && std::isfinite(p.max_prev) && std::fabs(p.min_prev) <= 1099511627776.0f &&
-            std::fabs(p.max_prev) <= 1099511627776.0f;
+void fill_filter_pair(SfPair& p, bool camera_ok, float fT_prev, float min_prev, float max_prev) {
+  bool ok = camera_ok && filter_const_ok(static_cast<double>(fT_prev)) && fT_prev != 0.0f && std::isfinite(min_prev) &&
+            std::isfinite(max_prev) && std::fabs(min_prev) <= 1099511627776.0f &&
+            std::fabs(max_prev) <= 1099511627776.0f;
   double rho = 0.0, tau = 0.0;
+  float Rf[9], tf[3];
   for (int k = 0; k < 9; k++) {
     ok = ok && filter_const_ok(p.R[k]);
-    p.Rf[k] = static_cast<float>(p.R[k]);
+    Rf[k] = static_cast<float>(p.R[k]);
     rho = std::fmax(rho, std::fabs(p.R[k]));
   }
   for (int k = 0; k < 3; k++) {
     ok = ok && filter_const_ok(p.t[k]);
-    p.tf[k] = static_cast<float>(p.t[k]);
+    tf[k] = static_cast<float>(p.t[k]);
     tau = std::fmax(tau, std::fabs(p.t[k]));
   }
-  p.rho = ok ? float_up(rho) : INFINITY;
+  p.r0 = make_float4(Rf[0], Rf[1], Rf[2], tf[0]);
+  p.r1 = make_float4(Rf[3], Rf[4], Rf[5], tf[1]);
+  p.r2 = make_float4(Rf[6], Rf[7], Rf[8], tf[2]);
+  p.g2.w = ok ? float_up(rho) : INFINITY;
   p.tau = ok ? float_up(tau) : INFINITY;
+}
+
+// The reference's disparity tests as closed intervals (common.cuh, SfPair).  getDisparity rejects d > max and
+// d < min (disparity_image_processor.cpp:25-28), so a NaN bound rejects nothing; getRightPoint additionally wants
+// 0 <= d < inf (scene_flow_constructor.h:220; -0.0f passes, and -0.0f >= 0.0f holds).
+struct DisparityBounds {
+  float lo_pt, hi_pt, lo_ch, hi_ch;
+};
+DisparityBounds fill_disparity_bounds(float dmin, float dmax) {
+  DisparityBounds b;
+  b.lo_pt = std::isnan(dmin) ? -INFINITY : dmin;
+  b.hi_pt = std::isnan(dmax) ? INFINITY : dmax;
+  b.lo_ch = b.lo_pt > 0.0f ? b.lo_pt : 0.0f;
+  b.hi_ch = b.hi_pt < 3.402823466e38f ? b.hi_pt : 3.402823466e38f;
+  return b;
 }
 
 bool same_camera(const mod_camera& a, const mod_camera& b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
@@ -237,6 +256,8 @@ int ensure_lut(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_camera& cam
 int check_size(mod_ctx* ctx, int w, int h, int batch) {
   if (!ctx) return MOD_ERR_INVALID_ARG;
   if (w <= 0 || h <= 0 || batch <= 0) return fail(ctx, MOD_ERR_INVALID_ARG, "non-positive size %dx%d batch %d", w, h, batch);
+  if (static_cast<long long>(w) * h >= (1ll << 30))  // the kernels index a frame (and its 2-float flow) with 32-bit ints
+    return fail(ctx, MOD_ERR_INVALID_ARG, "frame %dx%d has 2^30 pixels or more", w, h);
   if (w > ctx->max_w || h > ctx->max_h)
     return fail(ctx, MOD_ERR_INVALID_ARG, "frame %dx%d exceeds the context's %dx%d", w, h, ctx->max_w, ctx->max_h);
   if (batch > ctx->max_batch) return fail(ctx, MOD_ERR_INVALID_ARG, "batch %d exceeds the context's %d", batch, ctx->max_batch);
@@ -289,15 +310,14 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
       p.flow = src.flow_xy;
       fill_transform(src.prev2now, p);
       p.dt = src.dt_sec;
-      p.fT_now = src.f_now * src.T_now;  // float product, disparity_image_processor.cpp:43
-      p.min_now = src.min_disparity_now;
-      p.max_now = src.max_disparity_now;
-      p.fT_prev = src.f_prev * src.T_prev;
-      p.min_prev = src.min_disparity_prev;
-      p.max_prev = src.max_disparity_prev;
-      p.d_safe = safe_disparity(p, ray_x_max, ray_y_max);
-      fill_filter_pair(p, camera_ok);
-      p.pad = 0.0f;
+      const float fT_now = src.f_now * src.T_now;  // float product, disparity_image_processor.cpp:43
+      const float fT_prev = src.f_prev * src.T_prev;
+      const DisparityBounds bn = fill_disparity_bounds(src.min_disparity_now, src.max_disparity_now);
+      const DisparityBounds bp = fill_disparity_bounds(src.min_disparity_prev, src.max_disparity_prev);
+      p.g0 = make_float4(fT_now, bn.lo_pt, bn.hi_pt, bn.lo_ch);
+      p.g1 = make_float4(bn.hi_ch, fT_prev, bp.lo_pt, bp.hi_pt);
+      p.g2 = make_float4(bp.lo_ch, bp.hi_ch, safe_disparity(p, fT_prev, ray_x_max, ray_y_max), 0.0f);
+      fill_filter_pair(p, camera_ok, fT_prev, src.min_disparity_prev, src.max_disparity_prev);
     }
     L.first_frame = first;
     MOD_CK(ctx, launch_scene_flow(s, L, n));
@@ -489,6 +509,7 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   if (!out_ctx) return MOD_ERR_INVALID_ARG;
   *out_ctx = nullptr;
   if (max_w <= 0 || max_h <= 0 || max_batch <= 0 || max_clusters < 0) return MOD_ERR_INVALID_ARG;
+  if (static_cast<long long>(max_w) * max_h >= (1ll << 30)) return MOD_ERR_INVALID_ARG;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) return MOD_ERR_NO_DEVICE;
   cudaDeviceProp prop;

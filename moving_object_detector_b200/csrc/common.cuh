@@ -17,20 +17,24 @@ struct SfPair {
   const float* disp_now;   // dense 32FC1, device
   const float* disp_prev;  // dense 32FC1, device
   const float* flow;       // dense 32FC2, device
+  double dt;               // (stamp_now - stamp_prev).toSec()
+  // Hot per-pair scalars in 16-byte groups (one constant-bank load each).  The disparity tests of the reference
+  // (getDisparity's range test, getPoint3D's d != 0, getRightPoint's NaN / inf / negative test) are folded into
+  // closed intervals prepared on the host (abi.cu, fill_disparity_bounds):
+  //   "gives a point"  <=>  lo_pt <= d <= hi_pt  and  d != 0        (NaN fails both comparisons)
+  //   "usable in the chain" (range test and 0 <= d < inf)  <=>  lo_ch <= d <= hi_ch
+  float4 g0;               // fT_now (f*T in float, disparity_image_processor.cpp:43), lo_pt_now, hi_pt_now, lo_ch_now
+  float4 g1;               // hi_ch_now, fT_prev, lo_pt_prev, hi_pt_prev
+  float4 g2;               // lo_ch_prev, hi_ch_prev, d_safe, rho
+  float4 r0, r1, r2;       // float copies of (R[3i], R[3i+1], R[3i+2], t[i]) for the static-flow filter
+  float tau;               // >= max |t_i|; rho (g2.w) >= max |R_ij|; rho = +inf disables the filter for the pair
+  float pad[3];
   double R[9];             // row-major rotation, Eigen::Quaterniond::toRotationMatrix order of operations
   double t[3];
-  double dt;               // (stamp_now - stamp_prev).toSec()
-  float fT_now, min_now, max_now;     // f*T evaluated in float as at disparity_image_processor.cpp:43
-  float fT_prev, min_prev, max_prev;
-  float d_safe;            // previous disparities >= d_safe are known to ego-transform to a finite, non-NaN x
-  // float copies for the static-flow filter (sceneflow.cu, "filtered residual gate"); rho = +inf disables it
-  float rho;               // >= max |R_ij| (float copies)
-  float Rf[9], tf[3];
-  float tau;               // >= max |t_i|
-  float pad;
 };
+// d_safe (g2.z): previous disparities >= d_safe are known to ego-transform to a finite, non-NaN x
 
-constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 224 B = 14 KB of the 32 KB parameter space
+constexpr int kSfMaxPairsPerLaunch = 64;  // 64 * 240 B = 15 KB of the 32 KB parameter space
 
 struct SfLaunch {
   SfPair pair[kSfMaxPairsPerLaunch];
