@@ -20,13 +20,15 @@
 //
 // Pipeline (batched over frames); only cl_tile, cl_scatter (and the optional cl_labels) touch every dynamic pixel:
 //   cl_tile      one CTA per 32x32 tile.  Mask words + z of the tile and its N-pixel top/left halo are staged in shared
-//                memory; every dynamic pixel evaluates its window once (SIMD, see window_edges) and the surviving
-//                edges inside the tile are unioned in a shared-memory union-find.  The tile then publishes
-//                parent[pixel] = tile root, per-tile-root partial statistics (size, reference-order key, min/max of
-//                x,y,z; warp-shuffle reduced, then atomics), and three compact lists: dynamic pixels, pixels with an
-//                edge leaving the tile, tile roots.
-//   cl_merge     border list: the same window logic on global memory, lock-free union (atomicMin + path halving)
-//                of the edges that cross a tile border.  All union-find nodes touched here are tile roots.
+//                memory and every dynamic pixel evaluates its window once.  N in 1..4 (cl_tile_fast_kernel): pixels
+//                link to one accepted neighbour (a forest, no atomics), the forest is flattened and the remaining
+//                accepted edges are settled by label compares, with unions only where labels differ.  Other N
+//                (cl_tile_kernel): implied-edge elimination, then per-edge unions in a shared-memory union-find.
+//                The tile then publishes parent[pixel] = tile root, per-tile-root partial statistics (size,
+//                reference-order key, min/max of x,y,z; warp-shuffle reduced, then atomics), and three compact lists:
+//                dynamic pixels (with |v|), pixels with an edge leaving the tile, tile roots.
+//   cl_merge     border list: lock-free union (atomicMin + path halving) of the edges that cross a tile border,
+//                de-duplicated per warp to one union per distinct (tile root, tile root) pair.
 //   cl_roots     tile-root list: parent[r] = final root R; partial statistics of r are merged into R
 //   cl_slots     final roots with size >= cluster_size claim a dense survivor slot (removeSmallClusters)
 //   cl_rank      per frame: final ids by key rank, member-list offsets, work queue for cl_objects
@@ -250,22 +252,17 @@ constexpr uint8_t kDyn = 1;   // dynamic
 constexpr uint8_t kLeft = 2;  // edge to the left neighbour accepted  (both dynamic, depth gate passes)
 constexpr uint8_t kUp = 4;    // edge to the upper neighbour accepted
 
-// NC in 1..4 selects the fast path: per-pixel left/up edge bits are computed once per tile, horizontal runs are
-// labelled without any union-find traffic, the "implied edge" tests become a handful of bit operations on 25-bit
-// window masks, and a vertical unit edge is dropped when the 4-cycle p, p-(1,0), up(p)-(1,0), up(p) is closed by
-// accepted unit edges (its endpoints are then connected through the up-edge one pixel to the left, by induction on x).
-// NC == 0 is the generic path for N in 5..10 (runtime N, window_edges).
-template <int NC>
+// Generic tile kernel (neighbor_distance 0 and 5..10, runtime N): window_edges with the implied-edge elimination, then
+// per-edge unions in a shared-memory union-find.  neighbor_distance 1..4 (the default is 4) takes cl_tile_fast_kernel.
 __global__ void __launch_bounds__(kBlock)
     cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
-                   uint32_t* __restrict__ border_list,
-                   uint32_t* __restrict__ border_mask, uint32_t* __restrict__ root_list,
+                   uint32_t* __restrict__ border_list, uint32_t* __restrict__ root_list,
                    int* __restrict__ counters /* list, border, root */) {
+  constexpr int NC = 0;
   constexpr int kMaxN = 10;
-  constexpr int HN = NC > 0 ? NC : kMaxN;  // halo capacity
-  constexpr int SW = kTileW + HN;          // shared-memory row pitch
-  constexpr bool kFast = NC > 0;
-  const int N = NC > 0 ? NC : L.n;
+  constexpr int HN = kMaxN;        // halo capacity
+  constexpr int SW = kTileW + HN;  // shared-memory row pitch
+  const int N = L.n;
   const int stride = N + 1;
   __shared__ __align__(16) uint8_t s_m[(kTileH + HN) * SW];
   __shared__ float s_z[(kTileH + HN) * SW];
@@ -273,7 +270,6 @@ __global__ void __launch_bounds__(kBlock)
   __shared__ uint8_t s_up[kTileW * kTileH];  // pixel has an accepted up-left neighbour
   __shared__ uint16_t s_dl[kTileW * kTileH];
   __shared__ uint16_t s_bl[kTileW * kTileH];
-  __shared__ uint32_t s_bx[kFast ? kTileW * kTileH : 1];
   __shared__ uint16_t s_rl[kTileW * kTileH];
   __shared__ int s_cnt, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase;
   const int frame = blockIdx.z;
@@ -329,67 +325,18 @@ __global__ void __launch_bounds__(kBlock)
   }
   __syncthreads();
 
-  if constexpr (kFast) {
-    // A2: left / up edge bits of every staged dynamic pixel whose neighbour is staged too
-    constexpr int span = kTileW + NC;
-    uint8_t add[(span * span + kBlock - 1) / kBlock];
-#pragma unroll
-    for (int it = 0; it < (span * span + kBlock - 1) / kBlock; it++) {
-      const int k = it * kBlock + threadIdx.x;
-      add[it] = 0;
-      if (k < span * span) {
-        const int sy = k / span, sx = k - sy * span;
-        const int si = sy * SW + sx;
-        if (s_m[si]) {
-          const float z = s_z[si];
-          if (sx > 0 && s_m[si - 1] && depth_gate(z, s_z[si - 1], L.depth_thr)) add[it] |= kLeft;
-          if (sy > 0 && s_m[si - SW] && depth_gate(z, s_z[si - SW], L.depth_thr)) add[it] |= kUp;
-        }
-      }
-    }
-    __syncthreads();  // all dynamic bits read before any flag byte changes
-#pragma unroll
-    for (int it = 0; it < (span * span + kBlock - 1) / kBlock; it++) {
-      const int k = it * kBlock + threadIdx.x;
-      if (k < span * span && add[it]) {
-        const int sy = k / span, sx = k - sy * span;
-        s_m[sy * SW + sx] |= add[it];
-      }
-    }
-    __syncthreads();
-  }
-
   // B: initial labels and the tile-local list of dynamic pixels
   {
-    uint8_t f[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) f[j] = s_m[(row + N) * SW + N + wq * 4 + j];
     int lab4[4];
-    if constexpr (kFast) {
-      // horizontal runs: a pixel starts a run unless its left edge is accepted and the left pixel is in the core
-      uint32_t nib = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const bool starts = (f[j] & kDyn) && !((f[j] & kLeft) && (wq * 4 + j) > 0);
-        nib |= static_cast<uint32_t>(starts) << (wq * 4 + j);
-      }
-      // the 8 threads of a row are 8 consecutive lanes: OR-reduce their nibbles
-      nib |= __shfl_xor_sync(kFull, nib, 1);
-      nib |= __shfl_xor_sync(kFull, nib, 2);
-      nib |= __shfl_xor_sync(kFull, nib, 4);
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int lx = wq * 4 + j;
-        const uint32_t below = nib & ((2u << lx) - 1u);
-        lab4[j] = (f[j] & kDyn) ? row * kTileW + (31 - __clz(below)) : -1;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; j++) lab4[j] = (f[j] & kDyn) ? c0 + j : -1;
-    }
+    for (int j = 0; j < 4; j++) lab4[j] = ((word >> (8 * j)) & 0xffu) ? c0 + j : -1;
     *reinterpret_cast<int4*>(&s_lab[c0]) = make_int4(lab4[0], lab4[1], lab4[2], lab4[3]);
-#pragma unroll
-    for (int j = 0; j < 4; j++) smem_append((f[j] & kDyn) != 0, static_cast<uint16_t>(c0 + j), s_dl, &s_cnt);
+    // one warp appends one row at a time: 32 consecutive list entries are then (mostly) 32 consecutive pixels of a
+    // row, which keeps the shared-memory accesses of the later phases free of bank conflicts
+    for (int it = 0; it < kTileH / (kBlock / 32); it++) {
+      const int r = it * (kBlock / 32) + (threadIdx.x >> 5);
+      smem_append((s_m[(r + N) * SW + N + lane] & kDyn) != 0, static_cast<uint16_t>(r * kTileW + lane), s_dl, &s_cnt);
+    }
   }
   __syncthreads();
   const int nd = s_cnt;
@@ -400,7 +347,6 @@ __global__ void __launch_bounds__(kBlock)
     EdgeSetFor<NC> edges;
     edges.clear();
     int c = 0, lx = 0, ly = 0;
-    uint32_t cross = 0;  // fast path: window cells of the edges that leave the tile
     bool crosses = false;
     if (e < nd) {
       c = s_dl[e];
@@ -408,53 +354,13 @@ __global__ void __launch_bounds__(kBlock)
       lx = c & 31;
       const int sa = (ly + N) * SW + lx + N;
       const float z_here = s_z[sa];
-      if constexpr (kFast) {
-        constexpr int S = NC + 1;
-        constexpr int kA = NC * S + NC, kL = kA - 1, kU = kA - S;
-        uint32_t acc = 0, lm = 0, um = 0;
-#pragma unroll
-        for (int wy = 0; wy < S; wy++) {
-#pragma unroll
-          for (int wx = 0; wx < S; wx++) {
-            if (wy == NC && wx == NC) continue;
-            const int k = wy * S + wx;
-            const int si = (ly + wy) * SW + lx + wx;
-            const uint32_t f = s_m[si];
-            lm |= ((f >> 1) & 1u) << k;
-            um |= ((f >> 2) & 1u) << k;
-            if ((f & kDyn) && depth_gate(z_here, s_z[si], L.depth_thr)) acc |= 1u << k;
-          }
-        }
-        s_up[c] = acc != 0;
-        // cells whose right neighbour is still inside the window (wx < N)
-        uint32_t col_ok = 0;
-#pragma unroll
-        for (int wy = 0; wy < S; wy++) col_ok |= ((1u << NC) - 1u) << (wy * S);
-        uint32_t E = acc & ~(((acc & lm) >> 1) & col_ok) & ~((acc & um) >> S);
-        // unit edges: left is realised by the run labels inside the tile; up obeys the 4-cycle rule
-        const uint32_t own = s_m[sa];
-        const bool skip_up = (own & kLeft) && ((um >> kL) & 1u) && ((lm >> kU) & 1u);
-        if (skip_up) E &= ~(1u << kU);
-        if (lx > 0) E &= ~(1u << kL);
-        // split into tile-local and cross-tile edges: a cell (wx,wy) leaves the tile iff lx-N+wx < 0 or ly-N+wy < 0
-        uint32_t inside = 0;
-#pragma unroll
-        for (int wy = 0; wy < S; wy++) {
-          if (ly - NC + wy < 0) continue;
-          const int first = max(NC - lx, 0);  // wx >= first stays inside
-          if (first < S) inside |= ((((1u << S) - 1u) >> first) << first) << (wy * S);
-        }
-        cross = E & ~inside;
-        edges.w[0] = E & inside;
-      } else {
-        auto probe = [&](int wx, int wy, float& z) {
-          const int si = (ly + wy) * SW + lx + wx;
-          if (!s_m[si]) return false;
-          z = s_z[si];
-          return true;
-        };
-        s_up[c] = window_edges<NC>(N, z_here, L.depth_thr, probe, edges) ? 1 : 0;
-      }
+      auto probe = [&](int wx, int wy, float& z) {
+        const int si = (ly + wy) * SW + lx + wx;
+        if (!s_m[si]) return false;
+        z = s_z[si];
+        return true;
+      };
+      s_up[c] = window_edges<NC>(N, z_here, L.depth_thr, probe, edges) ? 1 : 0;
     }
     while (__any_sync(kFull, !edges.empty())) {  // warp-uniform loop: lanes stay converged between unions
       if (!edges.empty()) {
@@ -464,14 +370,11 @@ __global__ void __launch_bounds__(kBlock)
         if (nx >= 0 && ny >= 0)
           smem_union(s_lab, c, ny * kTileW + nx);
         else
-          crosses = true;  // generic path: the up-left endpoint lies in another tile, cl_merge recomputes
+          crosses = true;  // the up-left endpoint lies in another tile: cl_merge re-evaluates this pixel's window
       }
       __syncwarp();
     }
-    const int pos = smem_append(crosses || cross != 0, static_cast<uint16_t>(c), s_bl, &s_bcnt);
-    if constexpr (kFast) {
-      if (pos >= 0) s_bx[pos] = cross;
-    }
+    smem_append(crosses, static_cast<uint16_t>(c), s_bl, &s_bcnt);
   }
   __syncthreads();
 
@@ -565,11 +468,439 @@ __global__ void __launch_bounds__(kBlock)
   for (int e = threadIdx.x; e < nb; e += kBlock) {
     const int c = s_bl[e];
     border_list[s_bbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31));
-    if constexpr (kFast) border_mask[s_bbase + e] = s_bx[e];
   }
   for (int e = threadIdx.x; e < nr; e += kBlock) {
     const int c = s_rl[e];
     root_list[s_rbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + (c >> 5)) * L.w + tx0 + (c & 31));
+  }
+}
+
+// ---- cl_tile, fast path (N in 1..4) --------------------------------------------------------------------------------
+// Same contract as cl_tile_kernel (same outputs, same lists), different tile-local connectivity.  With noisy stereo
+// depth roughly every second depth gate between neighbours fails (measured on the 720p benchmark sequence: 48 % of the
+// unit edges accepted, 11 of 24 window cells accepted per dynamic pixel), so the window graph is a dense random graph
+// on which per-edge union-find operations are almost all redundant.  This kernel therefore
+//   C1  evaluates the window once per pixel (non-dynamic cells are staged as z = +inf, so a cell costs one shared load,
+//       one subtract and one compare) and LINKS the pixel to its raster-smallest accepted in-tile neighbour: a parent
+//       pointer to an earlier pixel, no atomics, no finds -- a spanning forest with a handful of trees per tile;
+//   F   flattens the forest (read-only finds);
+//   C2a compares the flattened label of every other accepted in-tile neighbour with the pixel's own (one shared load
+//       per edge) and unions ONE differing pair per pixel, de-duplicated per warp: this merges the trees;
+//   F   flattens again;
+//   C2b repeats the comparison and unions whatever still differs (rare).
+// Every accepted in-tile edge is either the link, found equal-labelled (endpoints in one set for certain: labels
+// only ever move towards the root), or unioned -- so the partition equals the one the reference's scan produces.
+// Pixels within N of the tile's top / left edge additionally run the implied-edge elimination of window_edges on their
+// cross-tile edges (they are listed separately so that interior warps do not pay for it).
+template <int NC>
+__global__ void __launch_bounds__(kBlock)
+    cl_tile_fast_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
+                        uint32_t* __restrict__ border_list, uint32_t* __restrict__ border_mask,
+                        uint32_t* __restrict__ root_list, int* __restrict__ counters /* list, border, root */) {
+  static_assert(NC >= 1 && NC <= 4, "fast path covers neighbor_distance 1..4");
+  constexpr int S = NC + 1;
+  constexpr int SW = kTileW + NC;  // shared-memory row pitch
+  constexpr int kA = NC * S + NC, kL = kA - 1, kU = kA - S;
+  constexpr int kPixels = kTileW * kTileH;
+  // A core pixel is identified by c = ly * SW + lx: the staged arrays' pitch, so that the window cell (wx, wy) of c is
+  // staged at c + wy * SW + wx, and so that neither 32 consecutive pixels of a row nor the NC leftmost pixels of
+  // consecutive rows (the two orders the lists below come in) collide on a shared-memory bank.
+  constexpr int kIds = kTileH * SW;
+  constexpr int kCore = NC * SW + NC;  // staged index of core pixel c is c + kCore
+  __shared__ __align__(16) uint8_t s_m[(kTileH + NC) * SW];
+  __shared__ float s_z[(kTileH + NC) * SW];
+  __shared__ int s_lab[kIds];
+  __shared__ uint8_t s_up[kIds];      // pixel has an accepted up-left neighbour
+  __shared__ uint32_t s_E[kIds];      // accepted in-tile window cells minus the link
+  __shared__ uint16_t s_dl[kPixels];  // interior pixels from the front, edge pixels from the back
+  __shared__ uint16_t s_bl[kPixels];
+  __shared__ uint32_t s_bx[kPixels];
+  __shared__ uint16_t s_rl[kPixels];
+  __shared__ int s_ni, s_ne, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase;
+  const int frame = blockIdx.z;
+  const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+  const size_t P = static_cast<size_t>(L.w) * L.h;
+  const size_t fb = frame * P;
+  const uint8_t* mask = L.mask + fb;
+  const float* pts = L.points + frame * L.points_frame_stride * 8;
+  const int lane = threadIdx.x & 31;
+  const float thr = L.depth_thr;
+  const bool thr_ok = thr < CUDART_INF_F;  // false for NaN too: then the +inf staging cannot stand in for "not dynamic"
+
+  if (threadIdx.x == 0) s_ni = s_ne = s_bcnt = s_rcnt = 0;
+
+  // A: the 32x32 core, one 4-pixel mask word per thread
+  const int row = threadIdx.x >> 3, wq = threadIdx.x & 7;
+  const int y = ty0 + row, x0 = tx0 + wq * 4;
+  uint32_t word = 0;
+  if (y < L.h && x0 < L.w) {
+    const uint8_t* src = mask + static_cast<size_t>(y) * L.w + x0;
+    if (x0 + 3 < L.w && (reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+      word = __ldg(reinterpret_cast<const uint32_t*>(src));
+    } else {
+      for (int j = 0; j < 4 && x0 + j < L.w; j++) word |= static_cast<uint32_t>(src[j]) << (8 * j);
+    }
+  }
+  if (!__syncthreads_or(word != 0)) return;  // no dynamic pixel in this tile
+
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const bool dyn = ((word >> (8 * j)) & 0xffu) != 0;
+    const int si = (row + NC) * SW + NC + wq * 4 + j;
+    s_m[si] = dyn ? kDyn : 0;
+    s_z[si] = dyn ? __ldg(pts + (static_cast<size_t>(y) * L.w + x0 + j) * 8 + 2) : CUDART_INF_F;
+  }
+  // halo: NC rows above (full width 32+NC) and NC columns to the left of the core
+  constexpr int top = NC * (kTileW + NC);
+  constexpr int n_halo = top + kTileH * NC;
+  for (int k = threadIdx.x; k < n_halo; k += kBlock) {
+    int sy, sx;
+    if (k < top) {
+      sy = k / (kTileW + NC);
+      sx = k - sy * (kTileW + NC);
+    } else {
+      const int k2 = k - top;
+      sy = NC + k2 / NC;
+      sx = k2 - (k2 / NC) * NC;
+    }
+    const int yy = ty0 - NC + sy, xx = tx0 - NC + sx;
+    uint8_t m = 0;
+    if (xx >= 0 && yy >= 0 && xx < L.w && yy < L.h) m = mask[static_cast<size_t>(yy) * L.w + xx] ? kDyn : 0;
+    s_m[sy * SW + sx] = m;
+    s_z[sy * SW + sx] = m ? __ldg(pts + (static_cast<size_t>(yy) * L.w + xx) * 8 + 2) : CUDART_INF_F;
+  }
+  __syncthreads();
+
+  // A2: left / up edge bits of the staged dynamic pixels in the halo band and the first NC core rows / columns:
+  // only the edge pixels' elimination reads them (flags of window cells, which lie at most NC inside the core)
+  {
+    constexpr int span = kTileW + NC;
+    constexpr int band = 2 * NC;  // staged rows / columns 0 .. 2*NC-1 hold every cell an edge pixel's window can touch
+    constexpr int n_band = band * span + (span - band) * band;
+    uint8_t add[(n_band + kBlock - 1) / kBlock];
+#pragma unroll
+    for (int it = 0; it < (n_band + kBlock - 1) / kBlock; it++) {
+      const int k = it * kBlock + threadIdx.x;
+      add[it] = 0;
+      if (k < n_band) {
+        int sy, sx;
+        if (k < band * span) {
+          sy = k / span;
+          sx = k - sy * span;
+        } else {
+          const int k2 = k - band * span;
+          sy = band + k2 / band;
+          sx = k2 - (k2 / band) * band;
+        }
+        const int si = sy * SW + sx;
+        if (s_m[si]) {
+          const float z = s_z[si];
+          if (sx > 0 && s_m[si - 1] && depth_gate(z, s_z[si - 1], thr)) add[it] |= kLeft;
+          if (sy > 0 && s_m[si - SW] && depth_gate(z, s_z[si - SW], thr)) add[it] |= kUp;
+        }
+      }
+    }
+    __syncthreads();  // all dynamic bits read before any flag byte changes
+#pragma unroll
+    for (int it = 0; it < (n_band + kBlock - 1) / kBlock; it++) {
+      const int k = it * kBlock + threadIdx.x;
+      if (k < n_band && add[it]) {
+        int sy, sx;
+        if (k < band * span) {
+          sy = k / span;
+          sx = k - sy * span;
+        } else {
+          const int k2 = k - band * span;
+          sy = band + k2 / band;
+          sx = k2 - (k2 / band) * band;
+        }
+        s_m[sy * SW + sx] |= add[it];
+      }
+    }
+  }
+
+  __syncthreads();  // flags complete
+  // B: the tile-local lists of dynamic pixels: interior pixels, and pixels within NC of the top / left tile edge.
+  // One warp appends one row at a time, so 32 consecutive list entries are (mostly) 32 consecutive pixels of a row.
+  {
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int it = 0; it < kTileH / (kBlock / 32); it++) {
+      const int r = it * (kBlock / 32) + warp;
+      const bool dyn = (s_m[(r + NC) * SW + NC + lane] & kDyn) != 0;
+      const bool edge = r < NC || lane < NC;
+      const uint16_t c = static_cast<uint16_t>(r * SW + lane);
+      smem_append(dyn && !edge, c, s_dl, &s_ni);
+      const unsigned ballot = __ballot_sync(kFull, dyn && edge);
+      if (ballot) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_ne, __popc(ballot));
+        base = __shfl_sync(kFull, base, 0);
+        if (dyn && edge) s_dl[kPixels - 1 - (base + __popc(ballot & ((1u << lane) - 1)))] = c;
+      }
+    }
+  }
+  __syncthreads();
+  const int ni = s_ni, ne = s_ne, nd = ni + ne;
+  {
+    // move the edge entries right behind the interior ones (source and destination may overlap: read, barrier, write)
+    uint16_t moved[(kPixels - (kTileW - NC) * (kTileH - NC) + kBlock - 1) / kBlock];
+#pragma unroll
+    for (int it = 0; it < static_cast<int>(sizeof(moved) / sizeof(moved[0])); it++) {
+      const int j = it * kBlock + threadIdx.x;
+      moved[it] = j < ne ? s_dl[kPixels - 1 - j] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < static_cast<int>(sizeof(moved) / sizeof(moved[0])); it++) {
+      const int j = it * kBlock + threadIdx.x;
+      if (j < ne) s_dl[ni + j] = moved[it];
+    }
+    __syncthreads();
+  }
+  auto pixel_at = [&](int e) -> int { return s_dl[e]; };
+
+  // window evaluation shared by both C1 loops: accepted cells of pixel c (window coordinates, bit k = wy*S+wx)
+  auto accepted_cells = [&](int c, float z_here) -> uint32_t {
+    uint32_t acc = 0;
+    if (thr_ok && fabsf(z_here) < CUDART_INF_F) {
+#pragma unroll
+      for (int wy = 0; wy < S; wy++) {
+#pragma unroll
+        for (int wx = 0; wx < S; wx++) {
+          if (wy == NC && wx == NC) continue;
+          // a non-dynamic cell holds +inf: |finite - inf| = inf > thr rejects it
+          if (!(fabsf(__fsub_rn(z_here, s_z[c + wy * SW + wx])) > thr)) acc |= 1u << (wy * S + wx);
+        }
+      }
+    } else {  // z_here not finite (foreign clouds) or no usable threshold: test the dynamic flag explicitly
+#pragma unroll
+      for (int wy = 0; wy < S; wy++) {
+#pragma unroll
+        for (int wx = 0; wx < S; wx++) {
+          if (wy == NC && wx == NC) continue;
+          const int si = c + wy * SW + wx;
+          if ((s_m[si] & kDyn) && depth_gate(z_here, s_z[si], thr)) acc |= 1u << (wy * S + wx);
+        }
+      }
+    }
+    return acc;
+  };
+  auto cell_offset = [](int k) -> int { return (k / S - NC) * SW + (k % S - NC); };
+
+  // C1, interior pixels: every window cell lies inside the tile
+  for (int e = threadIdx.x; e < ni; e += kBlock) {
+    const int c = s_dl[e];
+    const uint32_t acc = accepted_cells(c, s_z[c + kCore]);
+    s_up[c] = acc != 0;
+    s_lab[c] = acc ? c + cell_offset(__ffs(acc) - 1) : c;  // lowest bit = raster-smallest neighbour
+    s_E[c] = acc & (acc - 1);
+  }
+  // C1, edge pixels: cross-tile edges go to cl_merge after the implied-edge elimination
+  for (int e0 = 0; e0 < ne; e0 += kBlock) {
+    const int e = e0 + threadIdx.x;
+    uint32_t cross = 0;
+    int c = 0;
+    if (e < ne) {
+      c = pixel_at(ni + e);
+      const int ly = c / SW, lx = c - ly * SW;
+      const int sa = c + kCore;
+      const uint32_t acc = accepted_cells(c, s_z[sa]);
+      uint32_t lm = 0, um = 0;
+#pragma unroll
+      for (int wy = 0; wy < S; wy++) {
+#pragma unroll
+        for (int wx = 0; wx < S; wx++) {
+          if (wy == NC && wx == NC) continue;
+          const uint32_t f = s_m[c + wy * SW + wx];
+          lm |= ((f >> 1) & 1u) << (wy * S + wx);
+          um |= ((f >> 2) & 1u) << (wy * S + wx);
+        }
+      }
+      // cells whose right neighbour is still inside the window (wx < N)
+      uint32_t col_ok = 0;
+#pragma unroll
+      for (int wy = 0; wy < S; wy++) col_ok |= ((1u << NC) - 1u) << (wy * S);
+      uint32_t E = acc & ~(((acc & lm) >> 1) & col_ok) & ~((acc & um) >> S);
+      // the vertical unit edge is dropped when the 4-cycle p, p-(1,0), up(p)-(1,0), up(p) is closed by accepted unit
+      // edges: its endpoints are then connected through the up-edge one pixel to the left (induction on x)
+      const uint32_t own = s_m[sa];
+      if ((own & kLeft) && ((um >> kL) & 1u) && ((lm >> kU) & 1u)) E &= ~(1u << kU);
+      // a cell (wx,wy) leaves the tile iff lx-N+wx < 0 or ly-N+wy < 0
+      uint32_t inside = 0;
+#pragma unroll
+      for (int wy = 0; wy < S; wy++) {
+        if (ly - NC + wy < 0) continue;
+        const int first = max(NC - lx, 0);  // wx >= first stays inside
+        if (first < S) inside |= ((((1u << S) - 1u) >> first) << first) << (wy * S);
+      }
+      cross = E & ~inside;
+      const uint32_t local = acc & inside;
+      s_up[c] = acc != 0;
+      s_lab[c] = local ? c + cell_offset(__ffs(local) - 1) : c;
+      s_E[c] = local & (local - 1);
+    }
+    const int pos = smem_append(cross != 0, static_cast<uint16_t>(c), s_bl, &s_bcnt);
+    if (pos >= 0) s_bx[pos] = cross;
+  }
+  __syncthreads();
+
+  // labels of the accepted in-tile neighbours that differ from the pixel's own flattened label
+  auto differing = [&](int c, int my, uint32_t A) -> uint32_t {
+    uint32_t diff = 0;
+#pragma unroll
+    for (int k = 0; k < S * S - 1; k++)
+      if ((A >> k) & 1u) diff |= (s_lab[c + cell_offset(k)] != my) ? (1u << k) : 0u;
+    return diff;
+  };
+
+  for (int e = threadIdx.x; e < nd; e += kBlock) {  // F
+    const int c = pixel_at(e);
+    s_lab[c] = smem_find_readonly(s_lab, c);
+  }
+  __syncthreads();
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {  // C2a: one union per pixel, one lane per distinct (root, root) pair
+    const int e = e0 + threadIdx.x;
+    int my = -1, other = -1;
+    if (e < nd) {
+      const int c = pixel_at(e);
+      my = s_lab[c];
+      // (fully unrolled and predicated: measured faster than a loop that stops at the first differing label)
+      const uint32_t diff = differing(c, my, s_E[c]);
+      if (diff) other = s_lab[c + cell_offset(__ffs(diff) - 1)];
+    }
+    const unsigned has = __ballot_sync(kFull, other >= 0);
+    if (other >= 0) {
+      const int lo = min(my, other), hi = max(my, other);
+      const unsigned same = __match_any_sync(has, (lo << 11) | hi);
+      if (lane == __ffs(same) - 1) smem_union(s_lab, lo, hi);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nd; e += kBlock) {  // F
+    const int c = pixel_at(e);
+    s_lab[c] = smem_find_readonly(s_lab, c);
+  }
+  __syncthreads();
+  bool unioned = false;
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {  // C2b: whatever still differs
+    const int e = e0 + threadIdx.x;
+    int c = 0;
+    uint32_t diff = 0;
+    if (e < nd) {
+      c = pixel_at(e);
+      diff = differing(c, s_lab[c], s_E[c]);
+    }
+    unioned = unioned || diff != 0;
+    while (__any_sync(kFull, diff != 0)) {
+      if (diff) {
+        const int k = __ffs(diff) - 1;
+        diff &= diff - 1;
+        smem_union(s_lab, c, c + cell_offset(k));
+      }
+      __syncwarp();
+    }
+  }
+  const bool reflatten = __syncthreads_or(unioned);  // labels are flat unless C2b still had to union
+
+  // D1: flatten the tile-local forest; roots initialise their partial record
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {
+    const int e = e0 + threadIdx.x;
+    bool is_root = false;
+    int c = 0;
+    if (e < nd) {
+      c = pixel_at(e);
+      int r = s_lab[c];
+      if (reflatten) {
+        r = smem_find_readonly(s_lab, c);  // no halving stores here: see smem_find_readonly
+        s_lab[c] = r;
+      }
+      is_root = (r == c);
+      if (is_root) {
+        const size_t gi = fb + static_cast<size_t>(ty0 + c / SW) * L.w + tx0 + c % SW;
+        L.count[gi] = 0;
+        TileStat init;
+        init.key = 0x7fffffff;
+        init.mn[0] = init.mn[1] = init.mn[2] = 0xffffffffu;
+        init.mx[0] = init.mx[1] = init.mx[2] = 0u;
+        init.pad = 0;
+        L.tstat[gi] = init;
+      }
+    }
+    smem_append(is_root, static_cast<uint16_t>(c), s_rl, &s_rcnt);
+  }
+  __syncthreads();
+  const int nb = s_bcnt, nr = s_rcnt;
+  if (threadIdx.x == 0) {
+    s_base = atomicAdd(counters + 0, nd);
+    s_bbase = nb ? atomicAdd(counters + 1, nb) : 0;
+    s_rbase = atomicAdd(counters + 2, nr);
+    atomicAdd(L.n_dynamic + frame, nd);
+  }
+  __syncthreads();
+
+  // D2: publish parent = tile root, list entries, and the per-root partial statistics (pcl::getMinMax3D operands,
+  // size, reference-order key), reduced per tile root inside each warp (redux.sync) before the atomics
+  for (int e0 = 0; e0 < nd; e0 += kBlock) {
+    const int e = e0 + threadIdx.x;
+    int r = -1 - lane;  // distinct for idle lanes
+    uint32_t ex_mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, ex_mx[3] = {0u, 0u, 0u};
+    int key = 0x7fffffff;
+    if (e < nd) {
+      const int c = pixel_at(e);
+      r = s_lab[c];
+      const int i = (ty0 + c / SW) * L.w + tx0 + c % SW;
+      L.parent[fb + i] = (ty0 + r / SW) * L.w + tx0 + r % SW;
+      list[s_base + e] = static_cast<uint32_t>(fb + i);
+      const float4 xyz = __ldg(reinterpret_cast<const float4*>(pts + static_cast<size_t>(i) * 8));
+      // |v| (Vector3f::norm, the oracle's summation order) rides along with the list entry: the record's second half
+      // sits in the same 32-byte sector, and cl_scatter then reads 4 bytes per member instead of a sector
+      const float4 vel = __ldg(reinterpret_cast<const float4*>(pts + static_cast<size_t>(i) * 8 + 4));
+      list_speed[s_base + e] = __float_as_uint(__fsqrt_rn(
+          __fadd_rn(__fadd_rn(__fmul_rn(vel.x, vel.x), __fmul_rn(vel.y, vel.y)), __fmul_rn(vel.z, vel.z))));
+      const float cc[3] = {xyz.x, xyz.y, xyz.z};
+#pragma unroll
+      for (int k = 0; k < 3; k++)  // NaN coordinates are skipped (order dependent in the reference; unpinned)
+        if (!isnan(cc[k])) ex_mn[k] = ex_mx[k] = float_to_ordered(cc[k]);
+      if (s_up[c]) key = i;
+    }
+    unsigned todo = __ballot_sync(kFull, r >= 0);
+    while (todo) {  // peel one tile root at a time; usually one or two per warp
+      const int leader = __ffs(todo) - 1;
+      const int lr = __shfl_sync(kFull, r, leader);
+      const bool in = (r == lr);
+      const unsigned grp = __ballot_sync(kFull, in);
+      if (in) {
+        uint32_t mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          mn[k] = __reduce_min_sync(grp, ex_mn[k]);
+          mx[k] = __reduce_max_sync(grp, ex_mx[k]);
+        }
+        const int kk = __reduce_min_sync(grp, key);
+        if (lane == leader) {
+          const size_t gr = fb + static_cast<size_t>(ty0 + lr / SW) * L.w + tx0 + lr % SW;
+          atomicAdd(L.count + gr, __popc(grp));
+          TileStat& st = L.tstat[gr];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            if (mn[k] != 0xffffffffu) atomicMin(&st.mn[k], mn[k]);
+            if (mx[k] != 0u) atomicMax(&st.mx[k], mx[k]);
+          }
+          if (kk != 0x7fffffff) atomicMin(&st.key, kk);
+        }
+      }
+      todo &= ~grp;
+    }
+  }
+  for (int e = threadIdx.x; e < nb; e += kBlock) {
+    const int c = s_bl[e];
+    border_list[s_bbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + c / SW) * L.w + tx0 + c % SW);
+    border_mask[s_bbase + e] = s_bx[e];
+  }
+  for (int e = threadIdx.x; e < nr; e += kBlock) {
+    const int c = s_rl[e];
+    root_list[s_rbase + e] = static_cast<uint32_t>(fb + static_cast<size_t>(ty0 + c / SW) * L.w + tx0 + c % SW);
   }
 }
 
@@ -988,7 +1319,11 @@ template <int NC>
 void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint32_t* border_list, uint32_t* root_list,
                        int* counters) {
   const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
-  cl_tile_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list, counters);
+  if constexpr (NC > 0)
+    cl_tile_fast_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
+                                                     counters);
+  else
+    cl_tile_kernel<<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, root_list, counters);
   cl_merge_kernel<NC><<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
 }
 
