@@ -196,6 +196,21 @@ int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch,
                             size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params* params,
                             int32_t* d_opt_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats);
 
+/* ---- ~clusters_image ------------------------------------------------------------------------------------------ */
+/* ClustererNodelet::publishClustersImage (scene_flow_clusterer/src/clusterer_nodelet.cpp:293-322) with ColorSet
+ * (src/color_set.cpp:16-26): a BGR8 image, black where the label is -1 (NOT_BELONGED_), otherwise entry
+ * label * 255 / n_clusters of OpenCV's COLORMAP_HSV table (cv::applyColorMap, an un-vendored dependency; the table is
+ * generated from cv2 by tests/golden/make_colormap.py).  n_clusters is the number of surviving clusters of the frame
+ * (mod_frame_stats.n_clusters / *n_objs of mod_cluster), as in color_set_.resize(number_of_clusters_).
+ * Host seam: labels and out_bgr8 (w*h*3 bytes) are host pointers. */
+int mod_clusters_image(mod_ctx* ctx, int w, int h, const int32_t* labels, int32_t n_clusters, uint8_t* out_bgr8);
+/* Device-resident batch: d_labels batch*w*h, d_stats batch records (as written by mod_cluster_batched_dev),
+ * d_out_bgr8 batch*w*h*3 bytes.  Asynchronous on `stream`. */
+int mod_clusters_image_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const int32_t* d_labels,
+                                   const mod_frame_stats* d_stats, uint8_t* d_out_bgr8);
+/* The 256-entry COLORMAP_HSV table as 768 bytes (b, g, r). */
+void mod_host_hsv_colormap(uint8_t* bgr768);
+
 /* ---- static-flow filter (diagnostics) ------------------------------------------------------------------------ */
 /* The scene-flow kernel decides the residual gate (scene_flow_constructor.cpp:191-198) from a float evaluation of
  * the static flow with a rigorous error bound and re-evaluates undecided pixels with the reference's exact

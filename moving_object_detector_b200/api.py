@@ -97,6 +97,13 @@ class MovingObject:
     n_points: int
 
 
+def hsv_colormap() -> np.ndarray:
+    """The COLORMAP_HSV table the library embeds, (256, 3) uint8 BGR."""
+    out = np.empty((256, 3), np.uint8)
+    _lib.load().mod_host_hsv_colormap(out.ctypes.data)
+    return out
+
+
 def objects_from_records(rec: np.ndarray) -> List[MovingObject]:
     return [MovingObject(int(r["id"]), r["center"].astype(np.float64), r["velocity"].astype(np.float64),
                          r["bbox"].astype(np.float64), int(r["n_points"])) for r in rec]
@@ -211,6 +218,18 @@ class Context:
         res.status = rc
         res.n_objects = n.value
         return res
+
+    def clusters_image(self, labels: np.ndarray, n_clusters: int) -> np.ndarray:
+        """ClustererNodelet::publishClustersImage (clusterer_nodelet.cpp:293-322): (H,W) int32 labels -> (H,W,3) BGR8."""
+        labels = np.ascontiguousarray(labels, np.int32)
+        h, w = labels.shape
+        out = np.empty((h, w, 3), np.uint8)
+        self._check(self._lib.mod_clusters_image(self._h, w, h, labels.ctypes.data, int(n_clusters), out.ctypes.data))
+        return out
+
+    def clusters_image_batched_dev(self, w: int, h: int, batch: int, labels, stats, out_bgr8, stream: int = 0):
+        self._check(self._lib.mod_clusters_image_batched_dev(self._h, stream or None, w, h, batch, _dev_ptr(labels),
+                                                             _dev_ptr(stats), _dev_ptr(out_bgr8)))
 
     # ---- fused ----------------------------------------------------------------------------------------------
     def pipeline(self, now: DisparityImage, prev: DisparityImage, flow: np.ndarray, cam: CameraInfo,

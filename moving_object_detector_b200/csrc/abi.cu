@@ -715,6 +715,39 @@ int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch,
                          *params, d_opt_labels, d_objs, max_objs, d_stats);
 }
 
+int mod_clusters_image_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const int32_t* d_labels,
+                                   const mod_frame_stats* d_stats, uint8_t* d_out_bgr8) {
+  int rc = check_size(ctx, w, h, batch);
+  if (rc != MOD_OK) return rc;
+  if (!d_labels || !d_stats || !d_out_bgr8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  MOD_CK(ctx, launch_clusters_image(static_cast<cudaStream_t>(stream), d_labels, d_stats, 0, w, h, batch, d_out_bgr8));
+  ctx->launches++;
+  return MOD_OK;
+}
+
+int mod_clusters_image(mod_ctx* ctx, int w, int h, const int32_t* labels, int32_t n_clusters, uint8_t* out_bgr8) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!labels || !out_bgr8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  rc = ensure_host_staging(ctx);
+  if (rc != MOD_OK) return rc;
+  const size_t P = static_cast<size_t>(w) * h;
+  cudaStream_t s = ctx->stream;
+  uint8_t* d_bgr = reinterpret_cast<uint8_t*>(ctx->d_points);  // 32 bytes per pixel of staging, 3 needed
+  MOD_CK(ctx, cudaMemcpyAsync(ctx->d_labels, labels, P * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  MOD_CK(ctx, launch_clusters_image(s, ctx->d_labels, nullptr, n_clusters, w, h, 1, d_bgr));
+  ctx->launches++;
+  MOD_CK(ctx, cudaMemcpyAsync(out_bgr8, d_bgr, P * 3, cudaMemcpyDeviceToHost, s));
+  MOD_CK(ctx, cudaStreamSynchronize(s));
+  return MOD_OK;
+}
+
+void mod_host_hsv_colormap(uint8_t* bgr768) {
+  if (bgr768) host_hsv_colormap(bgr768);
+}
+
 int mod_pipeline_sequence_host(mod_ctx* ctx, int w, int h, int n_frames, const mod_camera* cam, float f, float T,
                                float min_disparity, float max_disparity, const float* disp_frames,
                                const float* flows, const mod_transform* transforms, const double* dt_sec,

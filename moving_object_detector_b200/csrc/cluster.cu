@@ -484,10 +484,11 @@ __global__ void __launch_bounds__(kBlock)
 //       one subtract and one compare) and LINKS the pixel to its raster-smallest accepted in-tile neighbour: a parent
 //       pointer to an earlier pixel, no atomics, no finds -- a spanning forest with a handful of trees per tile;
 //   F   flattens the forest (read-only finds);
-//   C2a compares the flattened label of every other accepted in-tile neighbour with the pixel's own (one shared load
-//       per edge) and unions ONE differing pair per pixel, de-duplicated per warp: this merges the trees;
+//   C2a compares the flattened label of the first remaining accepted in-tile neighbour with the pixel's own and
+//       unions the pair if they differ, de-duplicated per warp: the trees interleave, so this merges them;
 //   F   flattens again;
-//   C2b repeats the comparison and unions whatever still differs (rare).
+//   C2b compares the labels of ALL remaining accepted in-tile neighbours (one shared load per edge) and unions
+//       whatever still differs (rare).
 // Every accepted in-tile edge is either the link, found equal-labelled (endpoints in one set for certain: labels
 // only ever move towards the root), or unioned -- so the partition equals the one the reference's scan produces.
 // Pixels within N of the tile's top / left edge additionally run the implied-edge elimination of window_edges on their
@@ -765,9 +766,13 @@ __global__ void __launch_bounds__(kBlock)
     if (e < nd) {
       const int c = pixel_at(e);
       my = s_lab[c];
-      // (fully unrolled and predicated: measured faster than a loop that stops at the first differing label)
-      const uint32_t diff = differing(c, my, s_E[c]);
-      if (diff) other = s_lab[c + cell_offset(__ffs(diff) - 1)];
+      // only the first remaining accepted neighbour is looked at: the trees of the link forest interleave, so most
+      // pixels see another tree there, and any pair this round misses is settled by C2b
+      const uint32_t A = s_E[c];
+      if (A) {
+        const int lb = s_lab[c + cell_offset(__ffs(A) - 1)];
+        if (lb != my) other = lb;
+      }
     }
     const unsigned has = __ballot_sync(kFull, other >= 0);
     if (other >= 0) {
@@ -1308,6 +1313,32 @@ __global__ void __launch_bounds__(kBlock) cl_labels_kernel(const ClLaunch L) {
   }
 }
 
+// ---- cl_image ---------------------------------------------------------------------------------------------------
+// ~clusters_image (ClustererNodelet::publishClustersImage, clusterer_nodelet.cpp:293-322): BGR8, black for
+// NOT_BELONGED_, otherwise entry (label * 255 / n_clusters) of OpenCV's HSV colour map (ColorSet::resize,
+// color_set.cpp:16-26: input_map[i] = i * 255 / set_size, cv::applyColorMap(COLORMAP_HSV)).
+__constant__ uint32_t kHsvColormap[256] = {
+#include "hsv_colormap.inc"
+};
+
+__global__ void __launch_bounds__(kBlock)
+    cl_image_kernel(const int32_t* __restrict__ labels, const mod_frame_stats* __restrict__ stats, int fixed_n, size_t P,
+                    int batch, uint8_t* __restrict__ out_bgr) {
+  const size_t total = P * static_cast<size_t>(batch);
+  for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int label = labels[g];
+    uint32_t c = 0;  // (b, g, r) = (0, 0, 0)
+    if (label >= 0) {
+      const int n = stats ? stats[g / P].n_clusters : fixed_n;  // color_set_.resize(number_of_clusters_)
+      if (n > 0 && label < n) c = kHsvColormap[(static_cast<long long>(label) * 255 / n) & 255];
+    }
+    out_bgr[3 * g + 0] = static_cast<uint8_t>(c >> 16);
+    out_bgr[3 * g + 1] = static_cast<uint8_t>(c >> 8);
+    out_bgr[3 * g + 2] = static_cast<uint8_t>(c);
+  }
+}
+
 __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, size_t nc) {
   const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (t < na) a[t] = 0;
@@ -1328,6 +1359,26 @@ void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint
 }
 
 }  // namespace
+
+void host_hsv_colormap(uint8_t* bgr768) {
+  static const uint32_t table[256] = {
+#include "hsv_colormap.inc"
+  };
+  for (int i = 0; i < 256; i++) {
+    bgr768[3 * i + 0] = static_cast<uint8_t>(table[i] >> 16);
+    bgr768[3 * i + 1] = static_cast<uint8_t>(table[i] >> 8);
+    bgr768[3 * i + 2] = static_cast<uint8_t>(table[i]);
+  }
+}
+
+cudaError_t launch_clusters_image(cudaStream_t s, const int32_t* labels, const mod_frame_stats* stats, int fixed_n,
+                                  int w, int h, int batch, uint8_t* out_bgr) {
+  const size_t P = static_cast<size_t>(w) * h;
+  size_t blocks = (P * batch + kBlock - 1) / kBlock;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cl_image_kernel<<<static_cast<unsigned>(blocks), kBlock, 0, s>>>(labels, stats, fixed_n, P, batch, out_bgr);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, int* n_launches) {
   const size_t P = static_cast<size_t>(L.w) * L.h;

@@ -127,6 +127,11 @@ struct ClExtra {
 // Returns the number of kernels it launched through *n_launches.
 cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, int* n_launches);
 
+// ~clusters_image: labels (+ per-frame n_clusters from stats, or fixed_n when stats is null) -> BGR8
+cudaError_t launch_clusters_image(cudaStream_t s, const int32_t* labels, const mod_frame_stats* stats, int fixed_n,
+                                  int w, int h, int batch, uint8_t* out_bgr);
+void host_hsv_colormap(uint8_t* bgr768);
+
 // float threshold equivalents of the reference's float-vs-double comparisons
 float float_ceil_of_double(double th);   // smallest float >= th
 float float_floor_of_double(double th);  // largest float <= th

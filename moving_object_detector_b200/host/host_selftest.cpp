@@ -1,9 +1,10 @@
 // host_selftest.cpp -- drives the C++ host classes the way the ROS callbacks would.
 //   host_selftest --no-gpu                     checks that construction fails loudly without a GPU, the PointCloud2
 //                                              description and ros::Time arithmetic (runs in the CPU test-suite)
-//   host_selftest <case.bin> <out.bin>         runs construct() -> ~scene_flow -> dataCB() -> ~moving_objects on one
-//                                              frame pair read from case.bin and writes cloud + objects (GPU tests
-//                                              compare them with the oracle)
+//   host_selftest <case.bin> <out.bin>         runs construct() -> ~scene_flow -> dataCB() -> ~moving_objects,
+//                                              ~clusters_image, ~clusters on one frame pair read from case.bin and
+//                                              writes cloud + objects + image + markers (GPU tests compare them with
+//                                              the oracle)
 // case.bin: int32 w,h ; double cam[6] (fx,fy,cx,cy,Tx,Ty) ; float f,T,min,max ; double tr[7] ; uint32 sec0,nsec0,sec1,nsec1 ;
 //           int32 dynamic_flow_diff, cluster_size ; double depth_diff, dynamic_speed ; int32 neighbor_distance, pad ;
 //           float disp_prev[w*h], disp_now[w*h], flow[w*h*2]
@@ -110,10 +111,23 @@ int main(int argc, char** argv) {
     constructor.pc_with_velocity_pub_.publish = [&](const sensor_msgs::PointCloud2& m) { cloud = m; published++; };
     clusterer.dynamic_objects_pub_.publish = [&](const moving_object_msgs::MovingObjectArray& m) { objects = m; got_objects = true; };
     clusterer.dynamic_objects_pub_.num_subscribers = 1;
+    visualization_msgs::MarkerArray markers;
+    sensor_msgs::Image clusters_image;
+    int order = 0, markers_at = -1, image_at = -1;
+    clusterer.clusters_pub_.publish = [&](const visualization_msgs::MarkerArray& m) { markers = m; markers_at = order++; };
+    clusterer.clusters_image_pub_.publish = [&](const sensor_msgs::Image& m) { clusters_image = m; image_at = order++; };
     if (!constructor.construct(now, prev, flow, transform)) return fail(constructor.lastError().c_str());
     if (published != 1 || cloud.data.size() != P * 32) return fail("~scene_flow not published");
+    // unsubscribed visualisations must not be computed or published
     if (!clusterer.dataCB(cloud)) return fail(clusterer.lastError().c_str());
     if (!got_objects) return fail("~moving_objects not published");
+    if (markers_at >= 0 || image_at >= 0) return fail("visualisation published without a subscriber");
+    clusterer.clusters_pub_.num_subscribers = 1;
+    clusterer.clusters_image_pub_.num_subscribers = 1;
+    if (!clusterer.dataCB(cloud)) return fail(clusterer.lastError().c_str());
+    if (markers_at != 0 || image_at != 1) return fail("~clusters / ~clusters_image not published in the reference's order");
+    if (clusters_image.encoding != "bgr8" || clusters_image.step != w * 3 || clusters_image.data.size() != P * 3)
+      return fail("~clusters_image layout");
 
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return fail("cannot open output file");
@@ -124,6 +138,23 @@ int main(int argc, char** argv) {
       const double rec[10] = {static_cast<double>(m.id), m.center.position.x, m.center.position.y, m.center.position.z,
                               m.velocity.x, m.velocity.y, m.velocity.z, m.bounding_box.x, m.bounding_box.y, m.bounding_box.z};
       std::fwrite(rec, sizeof(double), 10, o);
+    }
+    // ~clusters_image, then ~clusters: int32 n_markers; per marker int32 id,type,action,n_points; float r,g,b,a;
+    // double scale x,y,z; n_points x 3 doubles
+    std::fwrite(clusters_image.data.data(), 1, clusters_image.data.size(), o);
+    const int32_t nm = static_cast<int32_t>(markers.markers.size());
+    std::fwrite(&nm, sizeof(nm), 1, o);
+    for (const auto& m : markers.markers) {
+      const int32_t head[4] = {m.id, m.type, m.action, static_cast<int32_t>(m.points.size())};
+      const float color[4] = {m.color.r, m.color.g, m.color.b, m.color.a};
+      const double scale[3] = {m.scale.x, m.scale.y, m.scale.z};
+      std::fwrite(head, sizeof(int32_t), 4, o);
+      std::fwrite(color, sizeof(float), 4, o);
+      std::fwrite(scale, sizeof(double), 3, o);
+      for (const auto& pt : m.points) {
+        const double xyz[3] = {pt.x, pt.y, pt.z};
+        std::fwrite(xyz, sizeof(double), 3, o);
+      }
     }
     std::fclose(o);
     std::printf("host_selftest: ok, %d moving objects\n", n);

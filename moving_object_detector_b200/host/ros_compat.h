@@ -2,7 +2,8 @@
 // headers are not available (this build image has no ROS).  Field names, types and order follow the .msg definitions
 // so that the host classes compile unchanged against the real headers on a ROS box (define MOD_HAVE_ROS there):
 //   std_msgs/Header, sensor_msgs/{Image,CameraInfo,PointField,PointCloud2,RegionOfInterest}, stereo_msgs/DisparityImage,
-//   geometry_msgs/{Vector3,Quaternion,Transform,Point,Pose}, moving_object_msgs/{MovingObject,MovingObjectArray}
+//   geometry_msgs/{Vector3,Quaternion,Transform,Point,Pose}, std_msgs/ColorRGBA, visualization_msgs/{Marker,MarkerArray}
+//   (the fields cluster2Marker sets), moving_object_msgs/{MovingObject,MovingObjectArray}
 //   (moving_object_msgs/msg/MovingObject.msg:1-7, MovingObjectArray.msg:1-2 in the reference tree).
 #pragma once
 #ifdef MOD_HAVE_ROS
@@ -12,6 +13,7 @@
 #include <sensor_msgs/Image.h>
 #include <sensor_msgs/PointCloud2.h>
 #include <stereo_msgs/DisparityImage.h>
+#include <visualization_msgs/MarkerArray.h>
 #else
 #include <array>
 #include <cstdint>
@@ -94,6 +96,26 @@ struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
 struct Transform { Vector3 translation; Quaternion rotation; };
 struct Pose { Point position; Quaternion orientation; };
 }  // namespace geometry_msgs
+namespace std_msgs {
+struct ColorRGBA { float r = 0, g = 0, b = 0, a = 0; };
+}
+namespace visualization_msgs {
+struct Marker {  // visualization_msgs/Marker.msg (the members the clusterer touches plus the ones between them)
+  enum { ARROW = 0, CUBE = 1, SPHERE = 2, CYLINDER = 3, LINE_STRIP = 4, LINE_LIST = 5, CUBE_LIST = 6, SPHERE_LIST = 7,
+         POINTS = 8 };
+  enum { ADD = 0, MODIFY = 0, DELETE = 2, DELETEALL = 3 };
+  std_msgs::Header header;
+  std::string ns;
+  int32_t id = 0;
+  int32_t type = 0;
+  int32_t action = 0;
+  geometry_msgs::Pose pose;
+  geometry_msgs::Vector3 scale;
+  std_msgs::ColorRGBA color;
+  std::vector<geometry_msgs::Point> points;
+};
+struct MarkerArray { std::vector<Marker> markers; };
+}  // namespace visualization_msgs
 namespace moving_object_msgs {
 struct MovingObject {
   int32_t id = 0;

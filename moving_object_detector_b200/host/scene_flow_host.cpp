@@ -188,7 +188,10 @@ void ClustererB200::reconfigureCB(const ClustererConfig& config, uint32_t /*leve
 
 bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
   last_error_.clear();
-  if (dynamic_objects_pub_.getNumSubscribers() <= 0) return true;  // nothing else on the hot path is subscribed
+  const bool want_markers = clusters_pub_.getNumSubscribers() > 0;
+  const bool want_image = clusters_image_pub_.getNumSubscribers() > 0;
+  const bool want_objects = dynamic_objects_pub_.getNumSubscribers() > 0;
+  if (!want_markers && !want_image && !want_objects) return true;  // nothing is subscribed
   // pcl::fromROSMsg maps fields by name; the constructor's cloud is the 32-byte record x@0 y@4 z@8 vx@16 vy@20 vz@24
   if (msg.point_step != 32 || msg.row_step != 32u * msg.width ||
       msg.data.size() < static_cast<size_t>(msg.row_step) * msg.height) {
@@ -209,12 +212,75 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
   const mod_cl_params p{cluster_size_th_, depth_diff_th_, dynamic_speed_th_, neighbor_distance_th_};
   std::vector<mod_object> objs(4096);
   int32_t n = 0;
+  const size_t n_points = static_cast<size_t>(msg.width) * msg.height;
+  std::vector<int32_t> labels;  // cluster_map_ after removeSmallClusters; only the visualisations need it on the host
+  if (want_markers || want_image) labels.resize(n_points);
   const int rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), msg.data.data(), &p,
-                             nullptr, objs.data(), static_cast<int32_t>(objs.size()), &n);
+                             labels.empty() ? nullptr : labels.data(), objs.data(), static_cast<int32_t>(objs.size()), &n);
   if (rc != MOD_OK) {
     last_error_ = ctxError(ctx_, "mod_cluster", rc);
     return false;
   }
+  // number_of_clusters_ after removeSmallClusters == clusters.size(); every survivor is accepted as an object (all
+  // its members satisfy |v| >= dynamic_speed, so does the median), hence n is that count.
+  if (want_markers) {  // publishClusters :269-291, cluster2Marker :119-145
+    uint8_t table[768];
+    mod_host_hsv_colormap(table);
+    visualization_msgs::MarkerArray clusters_msg;
+    visualization_msgs::Marker delete_marker;
+    delete_marker.action = visualization_msgs::Marker::DELETEALL;
+    clusters_msg.markers.push_back(delete_marker);
+    clusters_msg.markers.resize(static_cast<size_t>(n) + 1);
+    for (int32_t id = 0; id < n; id++) {
+      visualization_msgs::Marker& m = clusters_msg.markers[static_cast<size_t>(id) + 1];
+      const uint8_t* bgr = table + 3 * (id * 255 / n);  // ColorSet::resize(clusters.size()), color_set.cpp:21-25
+      m.header = msg.header;
+      m.id = id;
+      m.type = visualization_msgs::Marker::POINTS;
+      m.action = visualization_msgs::Marker::ADD;
+      m.scale.x = 0.05;
+      m.scale.y = 0.05;
+      m.scale.z = 0;
+      m.color.a = 1.0;
+      m.color.r = bgr[2] / 255.0;
+      m.color.g = bgr[1] / 255.0;
+      m.color.b = bgr[0] / 255.0;
+    }
+    // clusterMap2IndicesCluster :97-117: u outer / v inner, so that is the order of every marker's points
+    const float* pts = reinterpret_cast<const float*>(msg.data.data());
+    for (uint32_t u = 0; u < msg.width; u++) {
+      for (uint32_t v = 0; v < msg.height; v++) {
+        const size_t i = static_cast<size_t>(msg.width) * v + u;
+        const int32_t c = labels[i];
+        if (c < 0 || c >= n) continue;
+        geometry_msgs::Point pt;
+        pt.x = pts[8 * i];
+        pt.y = pts[8 * i + 1];
+        pt.z = pts[8 * i + 2];
+        clusters_msg.markers[static_cast<size_t>(c) + 1].points.push_back(pt);
+      }
+    }
+    clusters_pub_.publish(clusters_msg);
+  }
+  if (want_image) {  // publishClustersImage :293-322
+    sensor_msgs::Image image;
+    image.header.frame_id = msg.header.frame_id;
+    image.header.stamp = msg.header.stamp;
+    image.height = msg.height;
+    image.width = msg.width;
+    image.encoding = "bgr8";
+    image.is_bigendian = 0;
+    image.step = msg.width * 3;
+    image.data.resize(n_points * 3);
+    const int rc2 = mod_clusters_image(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), labels.data(), n,
+                                       image.data.data());
+    if (rc2 != MOD_OK) {
+      last_error_ = ctxError(ctx_, "mod_clusters_image", rc2);
+      return false;
+    }
+    clusters_image_pub_.publish(image);
+  }
+  if (!want_objects) return true;
   moving_object_msgs::MovingObjectArray out;
   out.header = msg.header;  // moving_objects_msg.header = input_header_, :327
   out.moving_object_array.resize(static_cast<size_t>(n));

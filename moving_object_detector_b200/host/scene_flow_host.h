@@ -105,12 +105,15 @@ class ClustererB200 {
 
   void reconfigureCB(const ClustererConfig& config, uint32_t level);  // clusterer_nodelet.cpp:345-352
 
-  // ClustererNodelet::dataCB (:221-242): ~moving_objects is computed and published when subscribed (:237-238).
-  // ~clusters / ~clusters_image are debug visualisations outside the hot path.
+  // ClustererNodelet::dataCB (:221-242): each output is computed and published only when subscribed (:233-238), in
+  // the reference's order ~clusters, ~clusters_image, ~moving_objects; one mod_cluster call serves all three (the
+  // label image is requested only when a visualisation is subscribed).
   // Returns false (and publishes nothing) on a malformed cloud or a GPU error.
   bool dataCB(const sensor_msgs::PointCloud2& input_pc_msg);
 
-  scene_flow_constructor::Sink<moving_object_msgs::MovingObjectArray> dynamic_objects_pub_;
+  scene_flow_constructor::Sink<visualization_msgs::MarkerArray> clusters_pub_;       // ~clusters        (:269-291)
+  scene_flow_constructor::Sink<sensor_msgs::Image> clusters_image_pub_;              // ~clusters_image  BGR8 (:293-322)
+  scene_flow_constructor::Sink<moving_object_msgs::MovingObjectArray> dynamic_objects_pub_;  // ~moving_objects
 
   const std::string& lastError() const { return last_error_; }
 

@@ -660,6 +660,63 @@ int orc_cluster(int w, int h, const float* points32, int32_t cluster_size, doubl
   return cl.collectMovingObjects(clusters, objs, max_objs, n_objs);
 }
 
+// ---- debug / visual side outputs of the clusterer ----------------------------------------------
+// ClustererNodelet::publishClustersImage (clusterer_nodelet.cpp:293-322) + ColorSet (color_set.cpp:11-26).  The
+// 256-entry table cv::applyColorMap(COLORMAP_HSV) maps through is OpenCV's (un-vendored); the caller passes it in
+// (tests use the fixture generated from cv2, tests/golden/hsv_colormap_bgr.npy).
+int orc_clusters_image(int w, int h, const int32_t* labels, int32_t number_of_clusters, const uint8_t* colormap_bgr768,
+                       uint8_t* out_bgr8) {
+  if (w <= 0 || h <= 0 || !labels || !colormap_bgr768 || !out_bgr8) return -1;
+  // ColorSet::resize(set_size): returns early for set_size < 1; input_map[i] = i * 255 / set_size; applyColorMap
+  std::vector<uint8_t> color_set;  // BGR per entry
+  if (number_of_clusters >= 1) {
+    color_set.resize(static_cast<size_t>(number_of_clusters) * 3);
+    for (int i = 0; i < number_of_clusters; i++) {
+      const uint8_t v = static_cast<uint8_t>(i * 255 / number_of_clusters);
+      for (int k = 0; k < 3; k++) color_set[3 * static_cast<size_t>(i) + k] = colormap_bgr768[3 * v + k];
+    }
+  }
+  const size_t n = static_cast<size_t>(w) * h;
+  for (size_t i = 0; i < n; i++) {
+    int b = 0, g = 0, r = 0;
+    const int cluster = labels[i];
+    if (cluster != -1) {  // NOT_BELONGED_
+      if (cluster < 0 || static_cast<size_t>(cluster) * 3 >= color_set.size()) return -3;  // cv::Mat::at out of range
+      b = color_set[3 * static_cast<size_t>(cluster)];
+      g = color_set[3 * static_cast<size_t>(cluster) + 1];
+      r = color_set[3 * static_cast<size_t>(cluster) + 2];
+    }
+    out_bgr8[3 * i] = static_cast<uint8_t>(b);  // cv::Vec3b(b, g, r)
+    out_bgr8[3 * i + 1] = static_cast<uint8_t>(g);
+    out_bgr8[3 * i + 2] = static_cast<uint8_t>(r);
+  }
+  return 0;
+}
+
+// clusterMap2IndicesCluster (clusterer_nodelet.cpp:97-117) on a final label map: per cluster the linear indices
+// W*v+u in u-outer / v-inner order -- the point order of the ~clusters markers (cluster2Marker :119-145).
+// out_offsets: number_of_clusters + 1 entries; out_indices: one entry per labelled pixel.
+int orc_cluster_members(int w, int h, const int32_t* labels, int32_t number_of_clusters, int32_t* out_offsets,
+                        int32_t* out_indices) {
+  if (w <= 0 || h <= 0 || !labels || number_of_clusters < 0 || !out_offsets || !out_indices) return -1;
+  std::vector<std::vector<int>> clusters(static_cast<size_t>(number_of_clusters));
+  for (int u = 0; u < w; u++) {
+    for (int v = 0; v < h; v++) {
+      const int c = labels[static_cast<size_t>(w) * v + u];
+      if (c == -1) continue;
+      if (c < 0 || c >= number_of_clusters) return -3;  // indices_clusters.at(cluster_number) would throw
+      clusters[static_cast<size_t>(c)].push_back(w * v + u);
+    }
+  }
+  int32_t pos = 0;
+  for (int c = 0; c < number_of_clusters; c++) {
+    out_offsets[c] = pos;
+    for (int i : clusters[static_cast<size_t>(c)]) out_indices[pos++] = i;
+  }
+  out_offsets[number_of_clusters] = pos;
+  return 0;
+}
+
 void orc_quat_to_matrix(const orc_transform* t, double* R9) {
   const Isometry iso = isometryFromTransform(*t);
   std::memcpy(R9, iso.R, sizeof(iso.R));

@@ -80,6 +80,16 @@ int orc_scene_flow_near(int w, int h, const orc_camera* cam, const orc_disparity
                         const float* flow_xy, int32_t flow_step_bytes, const orc_transform* prev2now,
                         int32_t dynamic_flow_diff, uint8_t* out_near);
 
+/* ~clusters_image: publishClustersImage (clusterer_nodelet.cpp:293-322) + ColorSet (color_set.cpp:11-26) on a final label
+ * map; colormap_bgr768 is OpenCV's COLORMAP_HSV table (256 x BGR).  Returns 0, -3 where cv::Mat::at would throw. */
+int orc_clusters_image(int w, int h, const int32_t* labels, int32_t number_of_clusters, const uint8_t* colormap_bgr768,
+                       uint8_t* out_bgr8);
+
+/* ~clusters marker point order: clusterMap2IndicesCluster (clusterer_nodelet.cpp:97-117), u outer / v inner.
+ * out_offsets has number_of_clusters + 1 entries, out_indices one entry per labelled pixel. */
+int orc_cluster_members(int w, int h, const int32_t* labels, int32_t number_of_clusters, int32_t* out_offsets,
+                        int32_t* out_indices);
+
 /* quaternion -> 3x3 rotation (row-major, 9 doubles), Eigen::Quaterniond::toRotationMatrix order of operations */
 void orc_quat_to_matrix(const orc_transform* t, double* R9);
 

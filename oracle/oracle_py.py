@@ -107,6 +107,34 @@ def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, nei
             "n_objects": n.value}
 
 
+def clusters_image(labels, number_of_clusters, colormap_bgr):
+    """publishClustersImage on a final label map; colormap_bgr: (256,3) uint8 COLORMAP_HSV table."""
+    lib = load()
+    labels = np.ascontiguousarray(labels, np.int32)
+    cm = np.ascontiguousarray(colormap_bgr, np.uint8)
+    h, w = labels.shape
+    out = np.empty((h, w, 3), np.uint8)
+    rc = lib.orc_clusters_image(w, h, C.c_void_p(labels.ctypes.data), C.c_int32(number_of_clusters),
+                                C.c_void_p(cm.ctypes.data), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"orc_clusters_image: {rc}")
+    return out
+
+
+def cluster_members(labels, number_of_clusters):
+    """clusterMap2IndicesCluster order (u outer / v inner): list of index arrays, one per cluster."""
+    lib = load()
+    labels = np.ascontiguousarray(labels, np.int32)
+    h, w = labels.shape
+    off = np.empty(number_of_clusters + 1, np.int32)
+    idx = np.empty(max(int((labels >= 0).sum()), 1), np.int32)
+    rc = lib.orc_cluster_members(w, h, C.c_void_p(labels.ctypes.data), C.c_int32(number_of_clusters),
+                                 C.c_void_p(off.ctypes.data), C.c_void_p(idx.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"orc_cluster_members: {rc}")
+    return [idx[off[c]:off[c + 1]].copy() for c in range(number_of_clusters)]
+
+
 def quat_to_matrix(transform):
     lib = load()
     t = Transform(*[float(v) for v in transform])

@@ -20,13 +20,15 @@ def main(path):
         scale = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}.get(u, 1.0)
         agg.setdefault(name, collections.OrderedDict()).setdefault(r[mi], []).append(v * scale)
     total = 0.0
-    print(f"{'kernel':28s} {'n':>3s} {'time_us':>10s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s} {'warp_inst':>14s}")
+    print(f"{'kernel':28s} {'n':>3s} {'time_us':>10s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s} {'warp_inst':>14s} "
+          f"{'l2_atom_sect':>13s} {'l2_red_sect':>12s}")
     for k, m in agg.items():
         mean = lambda key: (sum(m[key]) / len(m[key])) if key in m else float('nan')
         t = mean('gpu__time_duration.sum')
         total += t
         print(f"{k:28s} {len(m['gpu__time_duration.sum']):3d} {t:10.1f} {mean('dram__bytes_read.sum'):11.1f} "
-              f"{mean('dram__bytes_write.sum'):11.1f} {mean('smsp__inst_executed.sum'):14.0f}")
+              f"{mean('dram__bytes_write.sum'):11.1f} {mean('smsp__inst_executed.sum'):14.0f} "
+              f"{mean('lts__t_sectors_op_atom.sum'):13.0f} {mean('lts__t_sectors_op_red.sum'):12.0f}")
     print(f"sum of per-kernel means: {total:.1f} us")
 
 

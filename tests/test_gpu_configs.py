@@ -268,3 +268,40 @@ def test_full_batch_properties():
         # everything but the (tie-dependent) velocity pick must repeat exactly
         for f in ("id", "n_points", "center", "bbox"):
             assert np.array_equal(objs[i][:n][f], objs1[i][:n][f])
+
+
+# ---- debug / visual side outputs ---------------------------------------------------------------
+
+def test_clusters_image_matches_oracle(oracle):
+    """~clusters_image: host seam and device-resident batch against publishClustersImage restated in the oracle."""
+    import os
+    import torch
+    lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hsv_colormap_bgr.npy"))
+    cloud, _ = synth.make_stress_cloud(640, 400, seed=11, cluster_size=300)
+    want = oracle.cluster(cloud, 300, 0.15, 0.3, 4)
+    n = want["n_objects"]
+    assert n > 10
+    want_img = oracle.clusters_image(want["labels"], n, lut)
+    with Context(640, 400, max_batch=2) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=300))
+        assert np.array_equal(c.clusters_image(got.labels, got.n_objects), want_img)
+        # no clusters at all: everything black
+        assert (c.clusters_image(np.full((400, 640), -1, np.int32), 0) == 0).all()
+        # device-resident batch of two frames with different cluster counts
+        pts = torch.as_tensor(np.stack([cloud, cloud])).cuda().reshape(2, -1, 8)
+        pts[1, :, 4:7] = torch.where(torch.arange(640 * 400, device="cuda")[:, None] < 640 * 200, pts[1, :, 4:7],
+                                     torch.zeros((), device="cuda"))
+        lab = torch.empty((2, 640 * 400), dtype=torch.int32, device="cuda")
+        objs = torch.zeros((2, 256 * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        stats = torch.zeros((2, STATS_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        img = torch.empty((2, 400, 640, 3), dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.current_stream().cuda_stream
+        c.cluster_batched_dev(640, 400, 2, pts, None, ClustererConfig(cluster_size=300), objs, stats, 256, labels=lab,
+                              stream=stream)
+        c.clusters_image_batched_dev(640, 400, 2, lab, stats, img, stream=stream)
+        torch.cuda.synchronize()
+        st = stats.cpu().numpy().view(STATS_DTYPE).reshape(2)
+        labels = lab.cpu().numpy().reshape(2, 400, 640)
+        assert st[0]["n_clusters"] == n and 0 < st[1]["n_clusters"] < n
+        for i in range(2):
+            assert np.array_equal(img[i].cpu().numpy(), oracle.clusters_image(labels[i], int(st[i]["n_clusters"]), lut))

@@ -66,7 +66,22 @@ def test_host_mirror_frame_pair_equals_oracle(oracle, tmp_path):
     raw = open(out, "rb").read()
     cloud = np.frombuffer(raw[:w * h * 32], np.float32).reshape(h, w, 8)
     n = struct.unpack("<i", raw[w * h * 32:w * h * 32 + 4])[0]
-    objs = np.frombuffer(raw[w * h * 32 + 4:], np.float64).reshape(n, 10)
+    pos = w * h * 32 + 4
+    objs = np.frombuffer(raw[pos:pos + n * 80], np.float64).reshape(n, 10)
+    pos += n * 80
+    image = np.frombuffer(raw[pos:pos + w * h * 3], np.uint8).reshape(h, w, 3)
+    pos += w * h * 3
+    n_markers = struct.unpack("<i", raw[pos:pos + 4])[0]
+    pos += 4
+    markers = []
+    for _ in range(n_markers):
+        mid, mtype, action, npts = struct.unpack("<4i", raw[pos:pos + 16])
+        color = struct.unpack("<4f", raw[pos + 16:pos + 32])
+        scale = struct.unpack("<3d", raw[pos + 32:pos + 56])
+        pts = np.frombuffer(raw[pos + 56:pos + 56 + npts * 24], np.float64).reshape(npts, 3)
+        pos += 56 + npts * 24
+        markers.append((mid, mtype, action, color, scale, pts))
+    assert pos == len(raw)
     dt = 0.0 + 1e-9 * 33333333.0                                      # Duration.toSec(): sec + 1e-9 * nsec
     want = oracle.scene_flow(np.ascontiguousarray(disp[1]), np.ascontiguousarray(disp[0]), np.ascontiguousarray(flow),
                              cam, tr, dt, f=seq["f"], T=seq["T"], min_disparity=seq["min_disparity"],
@@ -78,3 +93,14 @@ def test_host_mirror_frame_pair_equals_oracle(oracle, tmp_path):
         assert int(got[0]) == exp["id"]
         assert np.array_equal(got[1:4].astype(np.float32), exp["center"])      # float -> float64 widening is lossless
         assert np.array_equal(got[7:10].astype(np.float32), exp["bbox"])
+    # ~clusters_image (publishClustersImage) and ~clusters (publishClusters / cluster2Marker)
+    lut = np.load(os.path.join(ROOT, "tests", "golden", "hsv_colormap_bgr.npy"))
+    assert np.array_equal(image, oracle.clusters_image(wc["labels"], n, lut))
+    members = oracle.cluster_members(wc["labels"], n)
+    assert n_markers == n + 1 and markers[0][2] == 3 and len(markers[0][5]) == 0          # DELETEALL first
+    flat = want["points32"].reshape(-1, 8)
+    for k, (mid, mtype, action, color, scale, pts) in enumerate(markers[1:]):
+        assert (mid, mtype, action) == (k, 8, 0) and scale == (0.05, 0.05, 0.0)           # POINTS, ADD
+        b, g, r = (int(v) for v in lut[k * 255 // n])
+        assert color == tuple(np.float32(v) for v in (r / 255.0, g / 255.0, b / 255.0, 1.0))
+        assert np.array_equal(pts, flat[members[k], :3].astype(np.float64))                # u-outer / v-inner order

@@ -200,3 +200,39 @@ def test_cluster_size_threshold_is_inclusive(oracle):
     assert r["n_objects"] == 2 and [o["n_points"] for o in r["objects"]] == [12, 12]
     r = oracle.cluster(pts, cluster_size=13, neighbor_distance=1)
     assert r["n_objects"] == 0
+
+
+def test_clusters_image_and_member_order(oracle):
+    """publishClustersImage / ColorSet (clusterer_nodelet.cpp:293-322, color_set.cpp:16-26) and the u-outer / v-inner
+    member order of clusterMap2IndicesCluster (:97-117) on a hand-made label map."""
+    import os
+    lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hsv_colormap_bgr.npy"))
+    labels = np.full((4, 5), -1, np.int32)
+    labels[0, 1:3] = 0
+    labels[1:4, 3] = 1
+    labels[3, 0] = 2
+    labels[1, 1] = 0
+    img = oracle.clusters_image(labels, 3, lut)
+    assert (img[labels == -1] == 0).all()
+    for k in range(3):
+        assert (img[labels == k] == lut[k * 255 // 3]).all()
+    members = oracle.cluster_members(labels, 3)
+    assert members[0].tolist() == [1, 6, 2]          # column 1 (rows 0, 1) before column 2
+    assert members[1].tolist() == [8, 13, 18] and members[2].tolist() == [15]
+    assert (oracle.clusters_image(labels * 0 - 1, 0, lut) == 0).all()   # no clusters: ColorSet::resize returns early
+    with pytest.raises(RuntimeError):
+        oracle.clusters_image(labels, 2, lut)        # label 2 with a 2-entry colour set: cv::Mat::at throws
+
+
+def test_embedded_colormap_equals_the_cv2_fixture(mod):
+    """The table compiled into libmod_b200.so is the fixture generated from cv2 (and equals cv2's if it is importable)."""
+    import os
+    from moving_object_detector_b200.api import hsv_colormap
+    lut = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hsv_colormap_bgr.npy"))
+    assert np.array_equal(hsv_colormap(), lut)
+    try:
+        import cv2
+    except ImportError:
+        return
+    live = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_HSV)[0]
+    assert np.array_equal(live, lut)
