@@ -297,6 +297,12 @@ def main_ours(args):
     st = np.frombuffer(stats.cpu().numpy().tobytes(), dtype=STATS_DTYPE)
     n_objects = int(st["n_objects"].sum())
     bad = int((st["status"] != 0).sum())
+    n_dynamic = int(st["n_dynamic"].sum())
+    # pixels of one step the filtered residual gate re-evaluated exactly (outside the timed region)
+    ctx.filter_fallbacks(reset=True)
+    step(False)
+    torch.cuda.synchronize()
+    filter_fallbacks = ctx.filter_fallbacks(reset=True)
 
     # ---- e2e through the host-buffer C-ABI call -----------------------------------------------------------------
     e2e = None
@@ -401,6 +407,11 @@ def main_ours(args):
             "e2e": e2e, "e2e_with_cloud": e2e_cloud,
             "cpu_baseline": cpu_baseline, "cpu_baseline_1thread": cpu_1thread,
             "gpu_launches": int(launches),
+            "clusterer": {"ms": elapsed_ms / args.steps - sf_mean_ms, "dynamic_pixels_per_step": n_dynamic,
+                          "note": "step time minus the scene-flow kernel: 8 clusterer kernels, per-kernel times and "
+                                  "L2 atomic sectors in profiles/r01_launches_summary.txt"},
+            "filter": {"exact_fallback_pixels_per_step": filter_fallbacks,
+                       "fraction_of_pixels": filter_fallbacks / float(P * B)},
             "objects_per_step": n_objects, "frames_with_error_status": bad,
             "clocks": clocks,
         }
