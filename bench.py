@@ -344,6 +344,8 @@ def main_ours(args):
         d2h = B * (MAX_OBJS * OBJECT_DTYPE.itemsize + STATS_DTYPE.itemsize)
         v = e2e_run(None)
         e2e = {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "h2d_gbs_per_gpu": h2d * (v / (B * world)) / 1e9,
+               "bound": "PCIe Gen5 x16 host-to-device link (55.5 GB/s measured, profiles/h2d_probe.cu)",
                "steps": e2e_steps, "api": "mod_pipeline_sequence_host (pinned host in, MovingObject lists out; "
                "the 32 B/px cloud stays on the GPU as it has no host subscriber)"}
         st_h = np.frombuffer(h_stats.numpy().tobytes(), dtype=STATS_DTYPE)
