@@ -305,3 +305,22 @@ def test_clusters_image_matches_oracle(oracle):
         assert st[0]["n_clusters"] == n and 0 < st[1]["n_clusters"] < n
         for i in range(2):
             assert np.array_equal(img[i].cpu().numpy(), oracle.clusters_image(labels[i], int(st[i]["n_clusters"]), lut))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("size", [(640, 400), (333, 217)])
+def test_every_neighbor_distance_path_matches_oracle(oracle, n, size):
+    """neighbor_distance 1..4 are separate instantiations of the fast tile kernel, 0 and >= 5 the generic kernel;
+    both on a frame of whole tiles and on one with ragged right / bottom tiles and an odd width."""
+    w, h = size
+    cloud, _ = synth.make_stress_cloud(w, h, seed=100 + n, cluster_size=200)
+    # depth noise of the order of depth_diff on half of the frame: the random-graph regime the fast kernel is built for
+    rng = np.random.RandomState(n)
+    cloud[:, : w // 2, 2] += rng.normal(0.0, 0.1, (h, w // 2)).astype(np.float32)
+    want = oracle.cluster(cloud, 200, 0.15, 0.3, n)
+    with Context(w, h) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=200, neighbor_distance=n), max_objs=1024)
+    assert np.array_equal(got.labels, want["labels"])
+    assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
+    if n > 0:
+        assert want["n_objects"] > 3
