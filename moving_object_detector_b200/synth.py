@@ -70,6 +70,13 @@ def _tri(x: float, lo: float, hi: float) -> float:
     return lo + (y if y <= span else 2 * span - y)
 
 
+def ros_dt(dt_sec: float) -> float:
+    """dt as a ROS node sees it: header stamps have nanosecond resolution and (stamp_now - stamp_prev).toSec() is
+    (double)sec + 1e-9 * (double)nsec (scene_flow_constructor.cpp:162-164)."""
+    sec, nsec = divmod(int(round(float(dt_sec) * 1e9)), 1000000000)
+    return float(sec) + 1e-9 * float(nsec)
+
+
 def make_sequence(cfg: SynthConfig, n_frames: int, device="cpu"):
     """Returns dict(disp (F,H,W) f32, flows (F-1,H,W,2) f32, transforms [(tx,ty,tz,qx,qy,qz,qw)], dts, cam, f, T,
     min_disparity, max_disparity)."""
@@ -101,7 +108,7 @@ def make_sequence(cfg: SynthConfig, n_frames: int, device="cpu"):
         Rs.append(R)
         ts.append(t)
         transforms.append((t[0], t[1], t[2], 0.0, math.sin(yaw / 2), 0.0, math.cos(yaw / 2)))
-        dts.append(cfg.dt)
+        dts.append(ros_dt(cfg.dt))
 
     # ---- back wall n.P = c in each frame (ground stays Y = cam_height under yaw + planar translation)
     n_wall, c_wall = [np.array([0.0, 0.0, 1.0])], [cfg.z_wall]

@@ -1,8 +1,10 @@
 // mod_oracle.cpp -- CPU ORACLE: a dependency-free restatement of the reference's hot path.
 //
-// TEST INFRASTRUCTURE ONLY (see mod_oracle.h).  PARITY STATUS: unpinned -- the reference has no tests and
-// cannot be built here; every function below cites the reference lines it restates (paths relative to
-// /root/reference) so it can be reviewed line-against-line.
+// TEST INFRASTRUCTURE ONLY (see mod_oracle.h).  PARITY STATUS: pinned to the reference's own code with shimmed
+// dependencies -- tests/test_reference_build.py requires every output below to equal, bit for bit, what the
+// reference's unmodified translation units publish when compiled against oracle/ref_shim/ (oracle/_ref/libmod_ref.so).
+// Every function cites the reference lines it restates (paths relative to /root/reference) so it can also be
+// reviewed line-against-line.
 //
 // Build: g++ -std=c++17 -O3 -DNDEBUG -msse3 -ffp-contract=off  (catkin Release + add_definitions(-msse3),
 // scene_flow_constructor/CMakeLists.txt:4).  x86-64 without -mfma never contracts a*b+c, and

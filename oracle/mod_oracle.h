@@ -5,11 +5,16 @@
  * link or call this.  Allowed users: tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline /
  * --impl reference legs (as the checker / the timed CPU baseline, never as the shipped path).
  *
- * PARITY STATUS: *unpinned*.  The reference (ROS Melodic + PCL + Eigen + OpenCV) cannot be compiled in
- * this image and ships no tests, golden vectors or fixtures.  This oracle is a
- * line-against-line restatement of the cited reference loops; the only piece validated against real
- * reference code is the label-equivalence table (oracle/_ref, built from
- * /root/reference/scene_flow_clusterer/src/lookup_table.cpp by oracle/Makefile).
+ * PARITY STATUS: *pinned to the reference's own code, with its third-party dependencies shimmed*.  The reference
+ * ships no tests, golden vectors or fixtures and its dependencies (ROS Melodic, PCL, Eigen, OpenCV) are not in this
+ * image, but its hot-path translation units compile UNMODIFIED, from where they lie under /root/reference, against
+ * the stand-in headers of oracle/ref_shim/ (oracle/Makefile target ref_full -> oracle/_ref/libmod_ref.so, driven by
+ * oracle/ref_full_wrap.cpp).  tests/test_reference_build.py requires this oracle to equal what
+ * SceneFlowConstructor::construct() and ClustererNodelet::dataCB() publish, bit for bit, on the golden fixtures
+ * (which are generated from that build), randomised and adversarial inputs; tests/test_gpu_reference.py compares
+ * the CUDA path with it directly.  What remains restated rather than executed is the arithmetic inside the
+ * un-vendored dependencies (image_geometry projection, tf2_eigen/Eigen products and norms, pcl::getMinMax3D, cv::Vec
+ * dot, the COLORMAP_HSV table taken from cv2): see the header of oracle/ref_shim/ref_shim.h and SURVEY.md Appendix B.
  *
  * The struct layouts deliberately equal those in include/mod_b200.h so that a test can hand the same
  * ctypes buffers to both sides, but the two headers share no code.

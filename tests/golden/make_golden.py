@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""Generates the committed golden fixtures tests/golden/*.npz.
+"""Generates the committed golden fixtures tests/golden/*.npz FROM THE REFERENCE'S OWN CODE.
 
-The reference ships no golden vectors and cannot be built or imported in this image, so these
-fixtures are produced by the CPU oracle (oracle/libmod_oracle.so) and frozen here; tests/test_golden.py checks that
-(1) the oracle still reproduces them, (2) the independent numpy restatement (tests/np_restatement.py) reproduces
-them and (3, -m gpu) the CUDA path reproduces them.  Re-run only when the oracle is deliberately changed:
+The reference ships no golden vectors.  Its hot-path translation units are compiled here, unmodified, from
+/root/reference against stand-in dependency headers (oracle/Makefile target ref_full -> oracle/_ref/libmod_ref.so,
+bound by oracle/ref_py.py); this script runs SceneFlowConstructor::construct() and ClustererNodelet::dataCB() on
+seeded inputs and freezes what the two nodes publish.  While generating, the CPU oracle (oracle/libmod_oracle.so) is
+required to agree bit for bit; only its per-pixel class image, which the reference does not expose, is taken from
+the oracle.  tests/test_golden.py then checks that (1) the oracle, (2) the independent numpy restatement
+(tests/np_restatement.py) and (3, -m gpu) the CUDA path reproduce the fixtures; tests/test_reference_build.py
+checks that the reference build still does.  Needs /root/reference (this container only):
 
-    python tests/golden/make_golden.py
+    make -C oracle && python tests/golden/make_golden.py
 """
 import dataclasses
 import os
@@ -19,6 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 
 import oracle_py  # noqa: E402
+import ref_py  # noqa: E402
 from moving_object_detector_b200 import synth  # noqa: E402
 
 
@@ -29,12 +34,26 @@ def scene_flow_case(name, cfg, pair=0, **kw):
     for key, fn in kw.items():
         if key == "mutate":
             fn(now, prev, flow)
-    tr, dt = np.asarray(seq["transforms"][pair], np.float64), float(seq["dts"][pair])
+    tr = np.asarray(seq["transforms"][pair], np.float64)
+    # ROS stamps have nanosecond resolution: dt is what (stamp_now - stamp_prev).toSec() returns for them
+    stamp_prev, stamp_now, dt = ref_py.stamps_for(float(seq["dts"][pair]))
     cam = np.asarray(seq["cam"], np.float64)
     meta = np.asarray([seq["f"], seq["T"], seq["min_disparity"], seq["max_disparity"]], np.float32)
     want = oracle_py.scene_flow(now, prev, flow, cam, tr, dt, dynamic_flow_diff=5, f=float(meta[0]), T=float(meta[1]),
                                 min_disparity=float(meta[2]), max_disparity=float(meta[3]), want_depth=True,
                                 want_static=True, want_class=True)
+    ref = ref_py.scene_flow(now, prev, flow, cam, tr, stamp_prev, stamp_now, dynamic_flow_diff=5, f=float(meta[0]),
+                            T=float(meta[1]), min_disparity=float(meta[2]), max_disparity=float(meta[3]))
+    assert ref["status"] == 0 and ref["published"] == 7
+    fields = [0, 1, 2, 4, 5, 6]
+    for a, b in ((ref["points32"][..., fields], want["points32"][..., fields]), (ref["depth"], want["depth"]),
+                 (ref["static_flow"], want["static_flow"])):
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint32),
+                                                                           b[~np.isnan(b)].view(np.uint32)), name
+    pts = ref["points32"].copy()
+    pts[..., 3] = 0.0   # the record's pad floats are uninitialised upstream
+    pts[..., 7] = 0.0
+    want = dict(want, points32=pts, depth=ref["depth"], static_flow=ref["static_flow"])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), disp_now=now, disp_prev=prev, flow=flow, cam=cam,
                         transform=tr, dt=np.float64(dt), meta=meta, dynamic_flow_diff=np.int32(5),
                         points32=want["points32"], depth=want["depth"], static_flow=want["static_flow"],
@@ -46,6 +65,13 @@ def scene_flow_case(name, cfg, pair=0, **kw):
 
 def cluster_case(name, cloud, **params):
     want = oracle_py.cluster(cloud, **params)
+    ref = ref_py.cluster(cloud, **params)
+    assert ref["status"] == 0 and ref["objects_lossless"]
+    assert np.array_equal(ref["labels"], want["labels"]) and np.array_equal(ref["dynamic"], want["dynamic"]), name
+    objects = ref["objects"].copy()
+    objects["n_points"] = [int((ref["labels"] == k).sum()) for k in objects["id"]]   # not in the message
+    assert objects.tobytes() == want["objects"].tobytes(), name
+    want = dict(want, labels=ref["labels"], dynamic=ref["dynamic"], objects=objects)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), points32=cloud,
                         params=np.asarray([params["cluster_size"], params["neighbor_distance"]], np.int32),
                         thresholds=np.asarray([params["depth_diff"], params["dynamic_speed"]], np.float64),

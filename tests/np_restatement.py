@@ -1,7 +1,7 @@
 """A SECOND, independent restatement of the hot path in numpy / pure Python, written from SURVEY.md Appendix A
-(not from oracle/mod_oracle.cpp).  Two restatements that were derived separately and agree bit for bit are the
-strongest pin available for an oracle whose reference (ROS Melodic + PCL + Eigen + OpenCV) cannot be built here and
-ships no tests.  Test infrastructure only; pure-Python loops are used for the clusterer, so keep images small.
+(not from oracle/mod_oracle.cpp).  The oracle is pinned to the reference's own code by tests/test_reference_build.py
+(oracle/_ref/libmod_ref.so); this second restatement, derived separately, additionally cross-checks the dependency
+arithmetic that the reference build has to shim.  Test infrastructure only; pure-Python loops are used for the clusterer, so keep images small.
 
 numpy float32 / float64 arithmetic is IEEE round-to-nearest-even per operation and never contracts to FMA, which is
 exactly the model of Appendix A ("f32(...)" narrowing, f64 ops without contraction).
