@@ -211,6 +211,33 @@ def main_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Multi-rank runs: keep this rank's threads -- and so the pinned host buffers it allocates (first touch) -- on the
+    NUMA node its GPU hangs off, so that eight concurrent host->device streams do not all read through one socket.
+    Returns a short description for the JSON line, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        sysfs = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        node = int(open(sysfs + "/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"node{node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -229,6 +256,7 @@ def main_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version / debug lines to stdout unless told otherwise; stdout carries the one JSON line
@@ -359,6 +387,7 @@ def main_ours(args):
         e2e = {"value": v, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "h2d_gbs_per_gpu": h2d * (v / (B * world)) / 1e9,
                "bound": "PCIe Gen5 x16 host-to-device link (55.5 GB/s measured, profiles/h2d_probe.cu)",
+               "host_numa_binding": numa,
                "steps": e2e_steps, "api": "mod_pipeline_sequence_host (pinned host in, MovingObject lists out; "
                "the 32 B/px cloud stays on the GPU as it has no host subscriber)"}
         st_h = np.frombuffer(h_stats.numpy().tobytes(), dtype=STATS_DTYPE)

@@ -30,6 +30,43 @@ static int runNoGpu() {
   if (pc.point_step != 32 || pc.row_step != 224 || pc.fields.size() != 6 || pc.fields[3].name != "vx" ||
       pc.fields[3].offset != 16 || pc.fields[5].offset != 24 || !pc.is_dense)
     return fail("PointCloud2 description");
+  {
+    // a foreign publisher's layout: 28-byte points {vz, x, intensity(u8 x4), y, vx, z, vy}, padded rows, no "vy" match
+    // (FLOAT64 datatype) -> fromROSMsg semantics: fields by name, the unmatched one stays 0
+        pc.data.assign(static_cast<size_t>(pc.row_step) * pc.height, 0);
+    if (cl::velocityCloudLayout(pc) != 1) return fail("native layout not recognised");
+    sensor_msgs::PointCloud2 other;
+    other.width = 5; other.height = 2; other.point_step = 28; other.row_step = 28 * 5 + 12;
+    const char* names[7] = {"vz", "x", "intensity", "y", "vx", "z", "vy"};
+    for (int i = 0; i < 7; i++) {
+      sensor_msgs::PointField f;
+      f.name = names[i]; f.offset = 4 * i; f.count = 1;
+      f.datatype = (i == 6) ? sensor_msgs::PointField::FLOAT64 : sensor_msgs::PointField::FLOAT32;
+      other.fields.push_back(f);
+    }
+    other.data.assign(static_cast<size_t>(other.row_step) * other.height, 0xAB);
+    for (uint32_t r = 0; r < 2; r++)
+      for (uint32_t c = 0; c < 5; c++)
+        for (int i = 0; i < 7; i++) {
+          const float v = 100.0f * r + 10.0f * c + i;
+          std::memcpy(&other.data[r * other.row_step + c * 28 + 4 * i], &v, 4);
+        }
+    if (cl::velocityCloudLayout(other) != 0) return fail("foreign layout not classified as repackable");
+    std::vector<uint8_t> rec;
+    cl::repackVelocityCloud(other, rec);
+    if (rec.size() != 10 * 32) return fail("repack size");
+    const float* q = reinterpret_cast<const float*>(rec.data());
+    for (uint32_t r = 0; r < 2; r++)
+      for (uint32_t c = 0; c < 5; c++) {
+        const float b = 100.0f * r + 10.0f * c;
+        const float* p = q + 8 * (r * 5 + c);
+        if (p[0] != b + 1 || p[1] != b + 3 || p[2] != b + 5 || p[3] != 0 || p[4] != b + 4 || p[5] != 0 || p[6] != b + 0 ||
+            p[7] != 0)
+          return fail("repack values");
+      }
+    other.data.resize(10);
+    if (cl::velocityCloudLayout(other) != -1) return fail("truncated cloud accepted");
+  }
   ros::Time a, b;
   a.sec = 10; a.nsec = 100000000;
   b.sec = 9;  b.nsec = 900000000;
@@ -128,6 +165,38 @@ int main(int argc, char** argv) {
     if (markers_at != 0 || image_at != 1) return fail("~clusters / ~clusters_image not published in the reference's order");
     if (clusters_image.encoding != "bgr8" || clusters_image.step != w * 3 || clusters_image.data.size() != P * 3)
       return fail("~clusters_image layout");
+
+    {
+      // the same cloud from a foreign publisher: packed 24-byte points in another field order, padded rows.  The
+      // nodelet maps fields by name (pcl::fromROSMsg), so the objects must be identical.
+      sensor_msgs::PointCloud2 other;
+      other.header = cloud.header;
+      other.width = w; other.height = h; other.point_step = 24; other.row_step = 24 * w + 8; other.is_dense = cloud.is_dense;
+      const char* names[6] = {"vx", "vy", "vz", "z", "y", "x"};
+      const int from[6] = {4, 5, 6, 2, 1, 0};
+      for (int i = 0; i < 6; i++) {
+        sensor_msgs::PointField fd;
+        fd.name = names[i]; fd.offset = 4 * i; fd.datatype = sensor_msgs::PointField::FLOAT32; fd.count = 1;
+        other.fields.push_back(fd);
+      }
+      other.data.assign(static_cast<size_t>(other.row_step) * h, 0xCD);
+      const float* src = reinterpret_cast<const float*>(cloud.data.data());
+      for (uint32_t r = 0; r < h; r++)
+        for (uint32_t c = 0; c < w; c++)
+          for (int i = 0; i < 6; i++)
+            std::memcpy(&other.data[static_cast<size_t>(r) * other.row_step + c * 24 + 4 * i],
+                        &src[8 * (static_cast<size_t>(r) * w + c) + from[i]], 4);
+      const moving_object_msgs::MovingObjectArray first = objects;
+      got_objects = false;
+      if (!clusterer.dataCB(other) || !got_objects) return fail("foreign PointCloud2 layout rejected");
+      if (objects.moving_object_array.size() != first.moving_object_array.size()) return fail("foreign layout: object count");
+      for (size_t i = 0; i < first.moving_object_array.size(); i++) {
+        const auto &a = first.moving_object_array[i], &b = objects.moving_object_array[i];
+        if (a.id != b.id || a.center.position.x != b.center.position.x || a.center.position.z != b.center.position.z ||
+            a.bounding_box.y != b.bounding_box.y || a.velocity.x != b.velocity.x || a.velocity.z != b.velocity.z)
+          return fail("foreign layout: objects differ");
+      }
+    }
 
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return fail("cannot open output file");

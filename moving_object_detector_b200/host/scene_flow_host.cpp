@@ -176,6 +176,47 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
 
 namespace scene_flow_clusterer {
 
+// The six FLOAT32 fields pcl::PointXYZVelocity registers (pcl_point_xyz_velocity.h:27-34) and their offsets in the record
+static const char* const kVelocityFieldNames[6] = {"x", "y", "z", "vx", "vy", "vz"};
+static const uint32_t kVelocityFieldOffsets[6] = {0, 4, 8, 16, 20, 24};
+
+// pcl's FieldMatches: same name, same datatype, same count (a count of 0 means 1)
+static const sensor_msgs::PointField* findVelocityField(const sensor_msgs::PointCloud2& msg, int i) {
+  const sensor_msgs::PointField* hit = nullptr;
+  for (const auto& f : msg.fields)
+    if (f.name == kVelocityFieldNames[i] && f.datatype == sensor_msgs::PointField::FLOAT32 && f.count <= 1) hit = &f;
+  return hit;
+}
+
+int velocityCloudLayout(const sensor_msgs::PointCloud2& msg) {
+  if (msg.data.size() < static_cast<size_t>(msg.row_step) * msg.height ||
+      static_cast<size_t>(msg.point_step) * msg.width > msg.row_step)
+    return -1;
+  bool native = msg.point_step == 32 && msg.row_step == 32u * msg.width;
+  for (int i = 0; i < 6; i++) {
+    const sensor_msgs::PointField* f = findVelocityField(msg, i);
+    if (f != nullptr && static_cast<size_t>(f->offset) + 4 > msg.point_step) return -1;
+    native = native && f != nullptr && f->offset == kVelocityFieldOffsets[i];
+  }
+  return native ? 1 : 0;
+}
+
+void repackVelocityCloud(const sensor_msgs::PointCloud2& msg, std::vector<uint8_t>& out) {
+  // fromPCLPointCloud2: points are value-initialised (all zero), then every registered field that has a match in the
+  // message is copied; a field without a match stays 0 ("Failed to find match for field")
+  const size_t n = static_cast<size_t>(msg.width) * msg.height;
+  out.assign(n * 32, 0);
+  for (int i = 0; i < 6; i++) {
+    const sensor_msgs::PointField* f = findVelocityField(msg, i);
+    if (f == nullptr) continue;
+    for (uint32_t r = 0; r < msg.height; r++) {
+      const uint8_t* src = msg.data.data() + static_cast<size_t>(r) * msg.row_step + f->offset;
+      uint8_t* dst = out.data() + static_cast<size_t>(r) * msg.width * 32 + kVelocityFieldOffsets[i];
+      for (uint32_t c = 0; c < msg.width; c++) std::memcpy(dst + static_cast<size_t>(c) * 32, src + static_cast<size_t>(c) * msg.point_step, 4);
+    }
+  }
+}
+
 ClustererB200::ClustererB200(int max_w, int max_h, int device) : ctx_(createContext(max_w, max_h, device)) {}
 ClustererB200::~ClustererB200() { mod_destroy(ctx_); }
 
@@ -192,30 +233,23 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
   const bool want_image = clusters_image_pub_.getNumSubscribers() > 0;
   const bool want_objects = dynamic_objects_pub_.getNumSubscribers() > 0;
   if (!want_markers && !want_image && !want_objects) return true;  // nothing is subscribed
-  // pcl::fromROSMsg maps fields by name; the constructor's cloud is the 32-byte record x@0 y@4 z@8 vx@16 vy@20 vz@24
-  if (msg.point_step != 32 || msg.row_step != 32u * msg.width ||
-      msg.data.size() < static_cast<size_t>(msg.row_step) * msg.height) {
-    last_error_ = "scene_flow cloud is not an organized PointXYZVelocity cloud with point_step 32";
+  // pcl::fromROSMsg (clusterer_nodelet.cpp:226) maps fields by name: the constructor's own cloud (32-byte records,
+  // x@0 y@4 z@8 vx@16 vy@20 vz@24, dense rows) is handed to the GPU as it is, any other layout is repacked first
+  std::vector<uint8_t> repacked;
+  const int layout = velocityCloudLayout(msg);
+  if (layout < 0) {
+    last_error_ = "scene_flow cloud: data is shorter than row_step * height, or a field lies outside point_step";
     return false;
   }
-  static const char* names[6] = {"x", "y", "z", "vx", "vy", "vz"};
-  static const uint32_t offsets[6] = {0, 4, 8, 16, 20, 24};
-  for (int i = 0; i < 6; i++) {
-    bool found = false;
-    for (const auto& f : msg.fields)
-      found = found || (f.name == names[i] && f.offset == offsets[i] && f.datatype == sensor_msgs::PointField::FLOAT32);
-    if (!found) {
-      last_error_ = std::string("scene_flow cloud lacks FLOAT32 field ") + names[i] + " at the expected offset";
-      return false;
-    }
-  }
+  if (layout == 0) repackVelocityCloud(msg, repacked);
+  const uint8_t* cloud = layout == 1 ? msg.data.data() : repacked.data();
   const mod_cl_params p{cluster_size_th_, depth_diff_th_, dynamic_speed_th_, neighbor_distance_th_};
   std::vector<mod_object> objs(4096);
   int32_t n = 0;
   const size_t n_points = static_cast<size_t>(msg.width) * msg.height;
   std::vector<int32_t> labels;  // cluster_map_ after removeSmallClusters; only the visualisations need it on the host
   if (want_markers || want_image) labels.resize(n_points);
-  const int rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), msg.data.data(), &p,
+  const int rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), cloud, &p,
                              labels.empty() ? nullptr : labels.data(), objs.data(), static_cast<int32_t>(objs.size()), &n);
   if (rc != MOD_OK) {
     last_error_ = ctxError(ctx_, "mod_cluster", rc);
@@ -247,7 +281,7 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
       m.color.b = bgr[0] / 255.0;
     }
     // clusterMap2IndicesCluster :97-117: u outer / v inner, so that is the order of every marker's points
-    const float* pts = reinterpret_cast<const float*>(msg.data.data());
+    const float* pts = reinterpret_cast<const float*>(cloud);
     for (uint32_t u = 0; u < msg.width; u++) {
       for (uint32_t v = 0; v < msg.height; v++) {
         const size_t i = static_cast<size_t>(msg.width) * v + u;

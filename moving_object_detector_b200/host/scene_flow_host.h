@@ -16,6 +16,7 @@
 #include <functional>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../../include/mod_b200.h"
 #include "ros_compat.h"
@@ -95,6 +96,13 @@ struct ClustererConfig {
   double dynamic_speed = 0.3;
   int neighbor_distance = 4;
 };
+
+// pcl::fromROSMsg<pcl::PointXYZVelocity> equivalents (clusterer_nodelet.cpp:226).  velocityCloudLayout: 1 = the
+// constructor's own layout (32-byte records, dense rows: usable in place), 0 = another layout that carries the fields
+// by name (repack), -1 = malformed.  repackVelocityCloud writes width*height records {x,y,z,0,vx,vy,vz,0}; a field the
+// message lacks (or carries with another datatype) stays 0, as in PCL.
+int velocityCloudLayout(const sensor_msgs::PointCloud2& msg);
+void repackVelocityCloud(const sensor_msgs::PointCloud2& msg, std::vector<uint8_t>& out);
 
 class ClustererB200 {
  public:
