@@ -211,6 +211,27 @@ int mod_clusters_image_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int
 /* The 256-entry COLORMAP_HSV table as 768 bytes (b, g, r). */
 void mod_host_hsv_colormap(uint8_t* bgr768);
 
+/* ---- image_crop (upstream glue) --------------------------------------------------------- */
+/* image_crop::ImageCrop::cameraCallback (image_crop/src/image_crop.cpp:20-43): the camera image, converted to bgr8 as
+ * cv_bridge::toCvShare(msg, "bgr8") does (:23; channel shuffles only), is cropped to target_w x target_h around the
+ * image centre: origin ((width - target_w) / 2, (height - target_h) / 2) in the reference's UNSIGNED 32-bit arithmetic
+ * (:24).  A window that does not lie inside the image makes the reference's cv::Mat ROI assertion throw (or, where
+ * cv::Rect's int sum overflows, read out of bounds); here it returns MOD_ERR_INVALID_ARG. */
+enum { MOD_ENC_BGR8 = 0, MOD_ENC_RGB8 = 1, MOD_ENC_BGRA8 = 2, MOD_ENC_RGBA8 = 3, MOD_ENC_MONO8 = 4 };
+/* Host seam: data = sensor_msgs/Image.data (h rows of step_bytes), out_bgr8 = target_w*target_h*3 bytes, dense. */
+int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int target_w,
+                   int target_h, uint8_t* out_bgr8);
+/* Device-resident batch: frame i starts at d_data + i*frame_stride_bytes; d_out_bgr8 = batch dense crops.
+ * Asynchronous on `stream`.  The source needs w, h <= the context's max_w, max_h. */
+int mod_image_crop_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, int encoding, const uint8_t* d_data,
+                               size_t frame_stride_bytes, int32_t step_bytes, int target_w, int target_h,
+                               uint8_t* d_out_bgr8);
+/* The CameraInfo fix-up of the same callback (:32-41), host only: K[2], P[2] = K[2] - (width - target_w) / 2 and
+ * K[5], P[6] = K[5] - (height - target_h) / 2 (both taken from K, unsigned quotients), everything else copied; the
+ * caller sets width / height to the target size.  Returns MOD_ERR_INVALID_ARG for a window outside the image. */
+int mod_host_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
+                              double* out_K9, double* out_P12);
+
 /* ---- static-flow filter (diagnostics) ------------------------------------------------------------------------ */
 /* The scene-flow kernel decides the residual gate (scene_flow_constructor.cpp:191-198) from a float evaluation of
  * the static flow with a rigorous error bound and re-evaluates undecided pixels with the reference's exact

@@ -115,6 +115,12 @@ PROTOTYPES = {
     "mod_clusters_image_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                  C.c_void_p, C.c_void_p]),
     "mod_host_hsv_colormap": (None, [C.c_void_p]),
+    "mod_image_crop": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int32, C.c_int, C.c_int,
+                                 C.c_void_p]),
+    "mod_image_crop_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_size_t, C.c_int32, C.c_int, C.c_int, C.c_void_p]),
+    "mod_host_crop_camera_info": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "mod_pipeline_sequence_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Camera), C.c_float,
                                              C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.POINTER(SfParams), C.POINTER(ClParams), C.c_void_p,

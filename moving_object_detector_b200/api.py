@@ -97,6 +97,24 @@ class MovingObject:
     n_points: int
 
 
+ENCODINGS = {"bgr8": 0, "rgb8": 1, "bgra8": 2, "rgba8": 3, "mono8": 4}  # MOD_ENC_* of include/mod_b200.h
+
+
+def crop_camera_info(w: int, h: int, target_w: int, target_h: int, K, P):
+    """The CameraInfo fix-up of ImageCrop::cameraCallback (image_crop/src/image_crop.cpp:32-41): returns (K', P');
+    the caller sets width / height to the target size.  Raises ModError for a window outside the image."""
+    lib = _lib.load()
+    K = np.ascontiguousarray(K, np.float64).ravel()
+    P = np.ascontiguousarray(P, np.float64).ravel()
+    assert K.size == 9 and P.size == 12
+    Ko, Po = np.empty(9), np.empty(12)
+    rc = lib.mod_host_crop_camera_info(int(w), int(h), int(target_w), int(target_h), K.ctypes.data, P.ctypes.data,
+                                       Ko.ctypes.data, Po.ctypes.data)
+    if rc != _lib.MOD_OK:
+        raise ModError(rc, "crop window does not lie inside the image")
+    return Ko, Po
+
+
 def hsv_colormap() -> np.ndarray:
     """The COLORMAP_HSV table the library embeds, (256, 3) uint8 BGR."""
     out = np.empty((256, 3), np.uint8)
@@ -230,6 +248,27 @@ class Context:
     def clusters_image_batched_dev(self, w: int, h: int, batch: int, labels, stats, out_bgr8, stream: int = 0):
         self._check(self._lib.mod_clusters_image_batched_dev(self._h, stream or None, w, h, batch, _dev_ptr(labels),
                                                              _dev_ptr(stats), _dev_ptr(out_bgr8)))
+
+    # ---- image_crop (upstream glue) ---------------------------------------------------------------------------
+    def image_crop(self, image: np.ndarray, encoding: str, target_w: int, target_h: int) -> np.ndarray:
+        """ImageCrop::cameraCallback's image part (image_crop/src/image_crop.cpp:20-30): (H,W[,C]) uint8 in `encoding`
+        (bgr8 / rgb8 / bgra8 / rgba8 / mono8; rows may be strided) -> (target_h, target_w, 3) bgr8."""
+        assert image.dtype == np.uint8 and image.strides[-1] == 1
+        h, w = image.shape[:2]
+        row_bytes = image[0].size if h else 0
+        step = image.strides[0] if h > 1 else row_bytes
+        buf = np.zeros((h, step), np.uint8)  # sensor_msgs/Image.data: h rows of `step` bytes
+        buf[:, :row_bytes] = image.reshape(h, row_bytes)
+        out = np.empty((max(target_h, 0), max(target_w, 0), 3), np.uint8)
+        self._check(self._lib.mod_image_crop(self._h, w, h, ENCODINGS[encoding], buf.ctypes.data, step, int(target_w),
+                                             int(target_h), out.ctypes.data))
+        return out
+
+    def image_crop_batched_dev(self, w: int, h: int, batch: int, encoding: str, data, frame_stride_bytes: int,
+                               step_bytes: int, target_w: int, target_h: int, out_bgr8, stream: int = 0):
+        self._check(self._lib.mod_image_crop_batched_dev(self._h, stream or None, w, h, batch, ENCODINGS[encoding],
+                                                         _dev_ptr(data), frame_stride_bytes, step_bytes, target_w,
+                                                         target_h, _dev_ptr(out_bgr8)))
 
     # ---- fused ----------------------------------------------------------------------------------------------
     def pipeline(self, now: DisparityImage, prev: DisparityImage, flow: np.ndarray, cam: CameraInfo,

@@ -744,6 +744,77 @@ int mod_clusters_image(mod_ctx* ctx, int w, int h, const int32_t* labels, int32_
   return MOD_OK;
 }
 
+// crop origin of image_crop.cpp:24 (uint32_t - int, unsigned division) and the ROI test of cv::Mat::operator()(Rect)
+static bool crop_window(uint32_t w, uint32_t h, int tw, int th, int* x0, int* y0) {
+  const uint32_t ox = (w - static_cast<uint32_t>(tw)) / 2u, oy = (h - static_cast<uint32_t>(th)) / 2u;
+  *x0 = static_cast<int>(ox);
+  *y0 = static_cast<int>(oy);
+  return *x0 >= 0 && tw >= 0 && static_cast<long long>(*x0) + tw <= static_cast<long long>(w) && *y0 >= 0 && th >= 0 &&
+         static_cast<long long>(*y0) + th <= static_cast<long long>(h);
+}
+
+int mod_image_crop_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, int encoding, const uint8_t* d_data,
+                               size_t frame_stride_bytes, int32_t step_bytes, int target_w, int target_h,
+                               uint8_t* d_out_bgr8) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  if (w <= 0 || h <= 0 || batch <= 0) return fail(ctx, MOD_ERR_INVALID_ARG, "bad image size or batch");
+  if (encoding < MOD_ENC_BGR8 || encoding > MOD_ENC_MONO8) return fail(ctx, MOD_ERR_INVALID_ARG, "unknown encoding %d", encoding);
+  static const int bpp_of[5] = {3, 3, 4, 4, 1};
+  if (step_bytes < w * bpp_of[encoding]) return fail(ctx, MOD_ERR_INVALID_ARG, "step %d shorter than a row", step_bytes);
+  int x0, y0;
+  if (!crop_window(static_cast<uint32_t>(w), static_cast<uint32_t>(h), target_w, target_h, &x0, &y0))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "crop window %dx%d does not lie inside the %dx%d image", target_w, target_h, w, h);
+  if (!d_data || (!d_out_bgr8 && target_w > 0 && target_h > 0)) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  MOD_CK(ctx, launch_image_crop(static_cast<cudaStream_t>(stream), d_data, frame_stride_bytes, step_bytes, encoding, x0,
+                                y0, target_w, target_h, batch, d_out_bgr8));
+  if (target_w > 0 && target_h > 0) ctx->launches++;
+  return MOD_OK;
+}
+
+int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int target_w,
+                   int target_h, uint8_t* out_bgr8) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!data) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  if (step_bytes <= 0 || static_cast<size_t>(step_bytes) > 16 * static_cast<size_t>(ctx->max_w))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "step %d outside (0, 16*max_w]", step_bytes);
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  rc = ensure_host_staging(ctx);
+  if (rc != MOD_OK) return rc;
+  // staging: the 32 bytes-per-pixel cloud buffer holds the source (at most 16 bytes per pixel of row stride) in its
+  // first half and the crop (3 bytes per pixel) in its second half
+  cudaStream_t s = ctx->stream;
+  uint8_t* d_src = reinterpret_cast<uint8_t*>(ctx->d_points);
+  uint8_t* d_out = d_src + 16 * static_cast<size_t>(ctx->max_w) * ctx->max_h;
+  MOD_CK(ctx, cudaMemcpyAsync(d_src, data, static_cast<size_t>(step_bytes) * h, cudaMemcpyHostToDevice, s));
+  rc = mod_image_crop_batched_dev(ctx, s, w, h, 1, encoding, d_src, 0, step_bytes, target_w, target_h, d_out);
+  if (rc != MOD_OK) return rc;
+  const size_t out_bytes = static_cast<size_t>(target_w) * target_h * 3;
+  if (out_bytes > 0) {
+    if (!out_bgr8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+    MOD_CK(ctx, cudaMemcpyAsync(out_bgr8, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  MOD_CK(ctx, cudaStreamSynchronize(s));
+  return MOD_OK;
+}
+
+int mod_host_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
+                              double* out_K9, double* out_P12) {
+  int x0, y0;
+  if (!K9 || !P12 || !out_K9 || !out_P12 || !crop_window(w, h, target_w, target_h, &x0, &y0)) return MOD_ERR_INVALID_ARG;
+  for (int i = 0; i < 9; i++) out_K9[i] = K9[i];
+  for (int i = 0; i < 12; i++) out_P12[i] = P12[i];
+  // image_crop.cpp:32-33: double - (uint32 quotient), both principal-point entries taken from K
+  const double cx = K9[2] - static_cast<double>(static_cast<uint32_t>(x0));
+  const double cy = K9[5] - static_cast<double>(static_cast<uint32_t>(y0));
+  out_K9[2] = cx;
+  out_K9[5] = cy;
+  out_P12[2] = cx;
+  out_P12[6] = cy;
+  return MOD_OK;
+}
+
 void mod_host_hsv_colormap(uint8_t* bgr768) {
   if (bgr768) host_hsv_colormap(bgr768);
 }

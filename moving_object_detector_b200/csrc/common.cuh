@@ -130,6 +130,10 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
 // ~clusters_image: labels (+ per-frame n_clusters from stats, or fixed_n when stats is null) -> BGR8
 cudaError_t launch_clusters_image(cudaStream_t s, const int32_t* labels, const mod_frame_stats* stats, int fixed_n,
                                   int w, int h, int batch, uint8_t* out_bgr);
+
+// glue.cu: image_crop (image_crop/src/image_crop.cpp:20-43).  encoding: MOD_ENC_* of include/mod_b200.h
+cudaError_t launch_image_crop(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding,
+                              int x0, int y0, int tw, int th, int batch, uint8_t* out);
 void host_hsv_colormap(uint8_t* bgr768);
 
 // float threshold equivalents of the reference's float-vs-double comparisons

@@ -198,6 +198,37 @@ int main(int argc, char** argv) {
       }
     }
 
+    {
+      // image_crop node: rgba8 camera image -> centred bgr8 crop + shifted principal point
+      const uint32_t tw = w / 2 + 1, th = h / 2;
+      image_crop::ImageCropB200 crop(static_cast<int>(w), static_cast<int>(h), static_cast<int>(tw), static_cast<int>(th));
+      sensor_msgs::Image src;
+      src.width = w; src.height = h; src.encoding = "rgba8"; src.step = w * 4 + 4;
+      src.data.resize(static_cast<size_t>(src.step) * h);
+      for (size_t i = 0; i < src.data.size(); i++) src.data[i] = static_cast<uint8_t>((i * 2654435761u) >> 13);
+      sensor_msgs::CameraInfo ci = info;
+      ci.K = {cam[0], 0, cam[2], 0, cam[1], cam[3], 0, 0, 1};
+      sensor_msgs::Image got;
+      sensor_msgs::CameraInfo got_info;
+      int n_pub = 0;
+      crop.camera_pub_ = [&](const sensor_msgs::Image& m, const sensor_msgs::CameraInfo& c) { got = m; got_info = c; n_pub++; };
+      if (!crop.cameraCallback(src, ci) || n_pub != 1) return fail(crop.lastError().c_str());
+      const uint32_t x0 = (w - tw) / 2, y0 = (h - th) / 2;
+      if (got.width != tw || got.height != th || got.step != tw * 3 || got.encoding != "bgr8") return fail("cropped image layout");
+      for (uint32_t r = 0; r < th; r++)
+        for (uint32_t c = 0; c < tw; c++) {
+          const uint8_t* p = &src.data[static_cast<size_t>(y0 + r) * src.step + (x0 + c) * 4];
+          const uint8_t* q = &got.data[static_cast<size_t>(r) * got.step + c * 3];
+          if (q[0] != p[2] || q[1] != p[1] || q[2] != p[0]) return fail("cropped pixels");
+        }
+      if (got_info.width != tw || got_info.height != th || got_info.K[2] != ci.K[2] - x0 || got_info.K[5] != ci.K[5] - y0 ||
+          got_info.P[2] != ci.K[2] - x0 || got_info.P[6] != ci.K[5] - y0 || got_info.P[0] != ci.P[0] || got_info.P[3] != ci.P[3])
+        return fail("cropped CameraInfo");
+      image_crop::ImageCropB200 too_big(static_cast<int>(w), static_cast<int>(h), static_cast<int>(w + 1), static_cast<int>(h));
+      too_big.camera_pub_ = crop.camera_pub_;
+      if (too_big.cameraCallback(src, ci) || n_pub != 1) return fail("a window larger than the image was published");
+    }
+
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return fail("cannot open output file");
     const int32_t n = static_cast<int32_t>(objects.moving_object_array.size());

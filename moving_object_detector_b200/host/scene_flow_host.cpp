@@ -341,3 +341,54 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
 }
 
 }  // namespace scene_flow_clusterer
+
+namespace image_crop {
+
+ImageCropB200::ImageCropB200(int max_w, int max_h, int target_width, int target_height, int device)
+    : ctx_(createContext(max_w, max_h, device)), target_width_(target_width), target_height_(target_height) {}
+
+ImageCropB200::~ImageCropB200() { mod_destroy(ctx_); }
+
+bool ImageCropB200::cameraCallback(const sensor_msgs::Image& image_msg, const sensor_msgs::CameraInfo& camera_info) {
+  last_error_.clear();
+  // cv_bridge::toCvShare(image_msg, "bgr8") (:23): the 8-bit colour encodings convert by channel shuffles
+  static const char* const names[5] = {"bgr8", "rgb8", "bgra8", "rgba8", "mono8"};
+  int encoding = -1;
+  for (int i = 0; i < 5; i++)
+    if (image_msg.encoding == names[i]) encoding = i;
+  if (encoding < 0) {
+    last_error_ = "image_crop: unsupported encoding " + image_msg.encoding;
+    return false;
+  }
+  if (image_msg.data.size() < static_cast<size_t>(image_msg.step) * image_msg.height) {
+    last_error_ = "image_crop: image data shorter than step * height";
+    return false;
+  }
+  sensor_msgs::CameraInfo cropped_caminfo = camera_info;  // :34
+  if (mod_host_crop_camera_info(image_msg.width, image_msg.height, target_width_, target_height_, camera_info.K.data(),
+                                camera_info.P.data(), cropped_caminfo.K.data(), cropped_caminfo.P.data()) != MOD_OK) {
+    last_error_ = "image_crop: the target window does not lie inside the image";
+    return false;
+  }
+  cropped_caminfo.width = static_cast<uint32_t>(target_width_);   // :39-40
+  cropped_caminfo.height = static_cast<uint32_t>(target_height_);
+  sensor_msgs::Image cropped;  // CvImage::toImageMsg of the bgr8 copy: dense rows
+  cropped.header = image_msg.header;
+  cropped.width = static_cast<uint32_t>(target_width_);
+  cropped.height = static_cast<uint32_t>(target_height_);
+  cropped.encoding = "bgr8";
+  cropped.is_bigendian = 0;
+  cropped.step = 3u * cropped.width;
+  cropped.data.resize(static_cast<size_t>(cropped.step) * cropped.height);
+  const int rc = mod_image_crop(ctx_, static_cast<int>(image_msg.width), static_cast<int>(image_msg.height), encoding,
+                                image_msg.data.data(), static_cast<int32_t>(image_msg.step), target_width_, target_height_,
+                                cropped.data.data());
+  if (rc != MOD_OK) {
+    last_error_ = ctxError(ctx_, "mod_image_crop", rc);
+    return false;
+  }
+  if (camera_pub_) camera_pub_(cropped, cropped_caminfo);  // :42
+  return true;
+}
+
+}  // namespace image_crop

@@ -135,3 +135,30 @@ class ClustererB200 {
 };
 
 }  // namespace scene_flow_clusterer
+
+// ---------------------------------------------------------------------------------------------------------------
+// image_crop::ImageCrop (image_crop/include/image_crop.h, src/image_crop.cpp:20-43): the node detect_with_zed.launch
+// puts in front of both cameras.  cameraCallback crops on the GPU through mod_image_crop and shifts the principal
+// point with mod_host_crop_camera_info; ~cropped_image carries bgr8 pixels and the adjusted CameraInfo.
+namespace image_crop {
+
+class ImageCropB200 {
+ public:
+  ImageCropB200(int max_w, int max_h, int target_width, int target_height, int device = 0);  // ~target_width / ~target_height
+  ~ImageCropB200();
+  ImageCropB200(const ImageCropB200&) = delete;
+  ImageCropB200& operator=(const ImageCropB200&) = delete;
+
+  // false (nothing published, lastError() says why) where the reference's cv::Mat ROI assertion would throw
+  bool cameraCallback(const sensor_msgs::Image& image_msg, const sensor_msgs::CameraInfo& camera_info);
+  const std::string& lastError() const { return last_error_; }
+
+  std::function<void(const sensor_msgs::Image&, const sensor_msgs::CameraInfo&)> camera_pub_;  // ~cropped_image
+
+ private:
+  mod_ctx* ctx_ = nullptr;
+  int target_width_, target_height_;
+  std::string last_error_;
+};
+
+}  // namespace image_crop

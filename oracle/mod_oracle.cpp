@@ -719,6 +719,52 @@ int orc_cluster_members(int w, int h, const int32_t* labels, int32_t number_of_c
   return 0;
 }
 
+// ---- image_crop ------------------------------------------------------------------------------------
+// ImageCrop::cameraCallback, image_crop/src/image_crop.cpp:20-43.  roi origin = (msg.width - target_width_) / 2 in
+// UNSIGNED 32-bit arithmetic (uint32_t - int), converted to int by cv::Rect; Mat::operator()(Rect) asserts the window
+// lies inside the image (:25-26).  cv_bridge::toCvShare(msg, "bgr8") (:23) converts other 8-bit encodings by channel
+// shuffles.  cropped_cx = K[2] - (double)((width - target_width_) / 2) with the same unsigned quotient (:32-33).
+static inline void crop_origin(uint32_t w, uint32_t h, int tw, int th, uint32_t* ox, uint32_t* oy) {
+  *ox = (w - static_cast<uint32_t>(tw)) / 2u;
+  *oy = (h - static_cast<uint32_t>(th)) / 2u;
+}
+
+int orc_image_crop(int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int target_w, int target_h,
+                   uint8_t* out_bgr8) {
+  static const int bpp_of[5] = {3, 3, 4, 4, 1};
+  static const int idx_of[5][3] = {{0, 1, 2}, {2, 1, 0}, {0, 1, 2}, {2, 1, 0}, {0, 0, 0}};  // source byte of B, G, R
+  if (encoding < 0 || encoding > 4 || !data || !out_bgr8) return -1;
+  uint32_t ox, oy;
+  crop_origin(static_cast<uint32_t>(w), static_cast<uint32_t>(h), target_w, target_h, &ox, &oy);
+  const int x0 = static_cast<int>(ox), y0 = static_cast<int>(oy);
+  if (!(0 <= x0 && 0 <= target_w && static_cast<long long>(x0) + target_w <= w && 0 <= y0 && 0 <= target_h &&
+        static_cast<long long>(y0) + target_h <= h))
+    return -12;
+  const int bpp = bpp_of[encoding];
+  for (int r = 0; r < target_h; r++)
+    for (int c = 0; c < target_w; c++) {
+      const uint8_t* p = data + static_cast<size_t>(y0 + r) * step_bytes + static_cast<size_t>(x0 + c) * bpp;
+      uint8_t* q = out_bgr8 + (static_cast<size_t>(r) * target_w + c) * 3;
+      q[0] = p[idx_of[encoding][0]];
+      q[1] = p[idx_of[encoding][1]];
+      q[2] = p[idx_of[encoding][2]];
+    }
+  return 0;
+}
+
+void orc_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
+                          double* out_K9, double* out_P12) {
+  uint32_t ox, oy;
+  crop_origin(w, h, target_w, target_h, &ox, &oy);
+  for (int i = 0; i < 9; i++) out_K9[i] = K9[i];
+  for (int i = 0; i < 12; i++) out_P12[i] = P12[i];
+  const double cx = K9[2] - static_cast<double>(ox), cy = K9[5] - static_cast<double>(oy);  // :32-33 (from K, also for P)
+  out_K9[2] = cx;
+  out_K9[5] = cy;
+  out_P12[2] = cx;
+  out_P12[6] = cy;
+}
+
 void orc_quat_to_matrix(const orc_transform* t, double* R9) {
   const Isometry iso = isometryFromTransform(*t);
   std::memcpy(R9, iso.R, sizeof(iso.R));

@@ -95,6 +95,15 @@ int orc_clusters_image(int w, int h, const int32_t* labels, int32_t number_of_cl
 int orc_cluster_members(int w, int h, const int32_t* labels, int32_t number_of_clusters, int32_t* out_offsets,
                         int32_t* out_indices);
 
+/* image_crop::ImageCrop::cameraCallback (image_crop/src/image_crop.cpp:20-43): centre crop to target_w x target_h of an
+ * 8-bit image converted to bgr8 (encoding 0 bgr8, 1 rgb8, 2 bgra8, 3 rgba8, 4 mono8) and the CameraInfo fix-up
+ * (K[2], K[5], P[2], P[6] shifted by the crop origin; width / height replaced).  Returns 0, or -12 where the
+ * reference's cv::Mat ROI assertion throws (crop window not inside the image). */
+int orc_image_crop(int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int target_w, int target_h,
+                   uint8_t* out_bgr8);
+void orc_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
+                          double* out_K9, double* out_P12);
+
 /* quaternion -> 3x3 rotation (row-major, 9 doubles), Eigen::Quaterniond::toRotationMatrix order of operations */
 void orc_quat_to_matrix(const orc_transform* t, double* R9);
 

@@ -135,6 +135,37 @@ def cluster_members(labels, number_of_clusters):
     return [idx[off[c]:off[c + 1]].copy() for c in range(number_of_clusters)]
 
 
+ENCODINGS = {"bgr8": 0, "rgb8": 1, "bgra8": 2, "rgba8": 3, "mono8": 4}
+
+
+def image_crop(image, encoding, target_w, target_h):
+    """ImageCrop::cameraCallback's image part: (H,W[,C]) uint8 in `encoding` -> (target_h,target_w,3) bgr8, or None where
+    the reference's ROI assertion throws."""
+    lib = load()
+    assert image.dtype == np.uint8 and image.strides[-1] == 1
+    h, w = image.shape[:2]
+    out = np.empty((max(target_h, 0), max(target_w, 0), 3), np.uint8)
+    lib.orc_image_crop.restype = C.c_int
+    rc = lib.orc_image_crop(w, h, ENCODINGS[encoding], C.c_void_p(image.ctypes.data), C.c_int32(image.strides[0]),
+                            C.c_int(target_w), C.c_int(target_h), C.c_void_p(out.ctypes.data))
+    if rc == -12:
+        return None
+    assert rc == 0, rc
+    return out
+
+
+def crop_camera_info(w, h, target_w, target_h, K, P):
+    lib = load()
+    K = np.ascontiguousarray(K, np.float64).ravel()
+    P = np.ascontiguousarray(P, np.float64).ravel()
+    Ko, Po = np.empty(9), np.empty(12)
+    lib.orc_crop_camera_info.restype = None
+    lib.orc_crop_camera_info(C.c_uint32(w), C.c_uint32(h), C.c_int(target_w), C.c_int(target_h),
+                             C.c_void_p(K.ctypes.data), C.c_void_p(P.ctypes.data), C.c_void_p(Ko.ctypes.data),
+                             C.c_void_p(Po.ctypes.data))
+    return Ko, Po
+
+
 def quat_to_matrix(transform):
     lib = load()
     t = Transform(*[float(v) for v in transform])

@@ -18,6 +18,7 @@
 
 #include "scene_flow_constructor.h"   // reference: scene_flow_constructor/include/scene_flow_constructor.h
 #include "clusterer_nodelet.h"        // reference: scene_flow_clusterer/include/clusterer_nodelet.h
+#include "image_crop.h"               // reference: image_crop/include/image_crop.h
 #include <sensor_msgs/PointCloud2.h>
 #include <visualization_msgs/MarkerArray.h>
 
@@ -284,6 +285,41 @@ int ref_cluster(int w, int h, const void* points32, int32_t cluster_size, double
     return rc;
   } catch (const std::out_of_range&) {
     return -10;
+  } catch (...) {
+    return -11;
+  }
+}
+
+/*
+ * image_crop::ImageCrop::cameraCallback (image_crop/src/image_crop.cpp:20-43) on one image + CameraInfo.
+ * encoding: 0 bgr8, 1 rgb8, 2 bgra8, 3 rgba8, 4 mono8.  K9 / P12: the CameraInfo matrices; out_K9 / out_P12 / out_wh
+ * receive the published CameraInfo's K, P, width, height; out_bgr8 the published image (dense target_w*target_h*3).
+ * Returns 0, -12 if the reference threw (ROI outside the image), -11 on another failure.
+ */
+int ref_image_crop(int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, const double* K9, const double* P12,
+                   int target_w, int target_h, uint8_t* out_bgr8, double* out_K9, double* out_P12, int32_t* out_wh) {
+  static const char* enc_names[5] = {"bgr8", "rgb8", "bgra8", "rgba8", "mono8"};
+  if (encoding < 0 || encoding > 4) return -11;
+  try {
+    ros::mod_ref_int_params() = {{"target_width", target_w}, {"target_height", target_h}};
+    image_crop::ImageCrop node;
+    sensor_msgs::ImagePtr img(new sensor_msgs::Image());
+    img->width = w; img->height = h; img->encoding = enc_names[encoding]; img->step = (uint32_t)step_bytes;
+    img->data.assign(data, data + (size_t)step_bytes * h);
+    sensor_msgs::CameraInfoPtr info(new sensor_msgs::CameraInfo());
+    info->width = w; info->height = h;
+    for (int i = 0; i < 9; i++) info->K[i] = K9[i];
+    for (int i = 0; i < 12; i++) info->P[i] = P12[i];
+    node.cameraCallback(img, info);
+    const image_transport::CameraPubState& st = *node.camera_pub_.state;
+    if (st.n_published != 1 || st.image.encoding != "bgr8") return -11;
+    if (out_bgr8) std::memcpy(out_bgr8, st.image.data.data(), std::min(st.image.data.size(), (size_t)target_w * target_h * 3));
+    for (int i = 0; i < 9 && out_K9; i++) out_K9[i] = st.info.K[i];
+    for (int i = 0; i < 12 && out_P12; i++) out_P12[i] = st.info.P[i];
+    if (out_wh) { out_wh[0] = st.info.width; out_wh[1] = st.info.height; out_wh[2] = st.image.width; out_wh[3] = st.image.height; out_wh[4] = st.image.step; }
+    return 0;
+  } catch (const std::runtime_error&) {
+    return -12;
   } catch (...) {
     return -11;
   }

@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from oracle_py import Camera, Disparity, Transform, _cam, _disp, OBJECT_DTYPE
+from oracle_py import Camera, Disparity, Transform, _cam, _disp, OBJECT_DTYPE, ENCODINGS
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libmod_ref.so")
@@ -34,7 +34,8 @@ def load():
     global _lib
     if _lib is None:
         _lib = C.CDLL(LIB_PATH)
-        for fn in ("ref_set_colormap", "ref_defaults", "ref_scene_flow", "ref_cluster", "ref_bench_pipeline"):
+        for fn in ("ref_set_colormap", "ref_defaults", "ref_scene_flow", "ref_cluster", "ref_bench_pipeline",
+                   "ref_image_crop"):
             getattr(_lib, fn).restype = C.c_int
         cm = np.ascontiguousarray(np.load(COLORMAP_PATH), np.uint8)
         assert cm.shape == (256, 3)
@@ -135,6 +136,27 @@ def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, nei
     return dict(status=rc, published=pub.value, dynamic=dyn, labels=labels, number_of_clusters=nclusters.value,
                 objects=rec, objects_raw=raw.copy(), objects_lossless=lossless, n_objects=n.value, clusters_image=bgr,
                 markers=markers, marker_rgba=mrgba[:m].copy(), n_markers=nm.value)
+
+
+def image_crop(image, encoding, target_w, target_h, K, P):
+    """image_crop::ImageCrop::cameraCallback on one image + CameraInfo.  Returns dict(status, image, K, P, width, height,
+    image_wh_step); status -12 = the reference threw (crop window outside the image)."""
+    lib = load()
+    assert image.dtype == np.uint8 and image.strides[-1] == 1
+    h, w = image.shape[:2]
+    out = np.zeros((max(target_h, 0), max(target_w, 0), 3), np.uint8)
+    K = np.ascontiguousarray(K, np.float64).ravel()
+    P = np.ascontiguousarray(P, np.float64).ravel()
+    Ko, Po, wh = np.zeros(9), np.zeros(12), np.zeros(5, np.int32)
+    row_bytes = image[0].size if h else 0
+    step = image.strides[0] if h > 1 else row_bytes
+    buf = np.zeros((h, step), np.uint8)   # the message's data: h rows of `step` bytes (padding zeroed)
+    buf[:, :row_bytes] = image.reshape(h, row_bytes)
+    rc = lib.ref_image_crop(w, h, ENCODINGS[encoding], C.c_void_p(buf.ctypes.data), C.c_int32(step),
+                            C.c_void_p(K.ctypes.data), C.c_void_p(P.ctypes.data), C.c_int(target_w), C.c_int(target_h),
+                            C.c_void_p(out.ctypes.data), C.c_void_p(Ko.ctypes.data), C.c_void_p(Po.ctypes.data),
+                            C.c_void_p(wh.ctypes.data))
+    return dict(status=rc, image=out, K=Ko, P=Po, width=int(wh[0]), height=int(wh[1]), image_wh_step=tuple(int(v) for v in wh[2:5]))
 
 
 def bench_pipeline(disp_frames, prev_index, now_index, flows, cam, transforms, dts, f, T, min_disparity,

@@ -8,6 +8,7 @@
 //   disparity_image_proc/src/disparity_image_processor.cpp
 //   scene_flow_constructor/src/scene_flow_constructor.cpp
 //   scene_flow_clusterer/src/{clusterer_nodelet,color_set,lookup_table}.cpp
+//   image_crop/src/image_crop.cpp
 // compile UNMODIFIED from where they lie under /root/reference into oracle/_ref/libmod_ref.so.  Every loop, branch,
 // cast and container access of the hot path is then the reference's; what is restated HERE is only the arithmetic that
 // lives in the un-vendored dependencies, each piece citing the upstream function it follows:
@@ -210,12 +211,22 @@ class Publisher {
   }
 };
 class Subscriber {};
+// integer parameters a test wants the nodes to find on the parameter server (image_crop's target_width / target_height)
+inline std::vector<std::pair<std::string, int>>& mod_ref_int_params() {
+  static thread_local std::vector<std::pair<std::string, int>> params;
+  return params;
+}
 class NodeHandle {
  public:
   NodeHandle() {}
   explicit NodeHandle(const std::string&) {}
   NodeHandle(const NodeHandle&, const std::string&) {}
   template <class T> bool getParam(const std::string&, T&) const { return false; }
+  bool getParam(const std::string& name, int& v) const {
+    for (const auto& kv : mod_ref_int_params())
+      if (kv.first == name) { v = kv.second; return true; }
+    return false;
+  }
   template <class T, class U> bool param(const std::string&, T& v, const U& d) const { v = d; return false; }
   std::string resolveName(const std::string& n) const { return n; }
   template <class M> Publisher advertise(const std::string& topic, uint32_t) {
@@ -268,6 +279,7 @@ typedef unsigned char uchar;
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
 namespace cv {
@@ -301,6 +313,11 @@ typedef Vec<uchar, 3> Vec3b;
 
 // cv::Mat restricted to 2-D; at<T>() indexes data + row*step + col*sizeof(T) exactly like core/mat.inl.hpp
 // (release builds do not bounds-check).  at<T>(i) on a continuous matrix is the linear element index.
+struct Rect {
+  int x = 0, y = 0, width = 0, height = 0;
+  Rect() {}
+  Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {}
+};
 struct MatStep {  // cv::MatStep: converts to size_t (bytes per row), step[0] is the same number
   size_t p[2] = {0, 0};
   MatStep() {}
@@ -333,6 +350,21 @@ class Mat {
   template <class T> const T& at(int r, int c) const { return *(const T*)(data + (size_t)r * step + (size_t)c * sizeof(T)); }
   template <class T> T& at(Point2i p) { return at<T>(p.y, p.x); }
   template <class T> const T& at(Point2i p) const { return at<T>(p.y, p.x); }
+  // Mat::operator()(const Rect&): a view into the same pixels; core/src/matrix.cpp asserts the ROI lies inside
+  Mat operator()(const Rect& r) const {
+    // (OpenCV evaluates roi.x + roi.width in int; where that overflows its behaviour is undefined -- evaluated in 64 bits here)
+    if (!(0 <= r.x && 0 <= r.width && (long long)r.x + r.width <= cols && 0 <= r.y && 0 <= r.height &&
+          (long long)r.y + r.height <= rows))
+      throw std::runtime_error("cv::Mat::Mat(roi): assertion failed, roi outside the matrix");
+    Mat m(*this);
+    m.rows = r.height; m.cols = r.width;
+    m.data = data + (size_t)r.y * step + (size_t)r.x * elemSize();
+    return m;
+  }
+  void copyTo(Mat& dst) const {
+    dst.create(rows, cols, type_);
+    for (int r = 0; r < rows; r++) std::memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * elemSize());
+  }
   template <class T> T& at(int i0) {
     if (isContinuous() || rows == 1) return ((T*)data)[i0];
     if (cols == 1) return *(T*)(data + (size_t)i0 * step);
@@ -388,22 +420,73 @@ class CvImage {
 typedef std::shared_ptr<CvImage> CvImagePtr;
 typedef std::shared_ptr<const CvImage> CvImageConstPtr;
 inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr&, const std::string&) { return CvImagePtr(); }  // upstream glue, never run
+// cv_bridge::toCvShare(msg, "bgr8") (cv_bridge/src/cv_bridge.cpp): shares the message's pixels when the encodings are
+// equal, otherwise converts with cv::cvtColor.  The colour conversions among 8-bit bgr8 / rgb8 / bgra8 / rgba8 / mono8
+// are pure channel shuffles (RGB2BGR swaps, BGRA2BGR drops alpha, GRAY2BGR replicates), restated here.
+inline CvImageConstPtr toCvShare(const sensor_msgs::ImageConstPtr& src, const std::string& encoding) {
+  if (encoding != "bgr8") throw std::runtime_error("ref_shim: toCvShare only to bgr8");
+  CvImagePtr out = std::make_shared<CvImage>();
+  out->header = src->header;
+  out->encoding = encoding;
+  const int h = (int)src->height, w = (int)src->width;
+  uint8_t* base = const_cast<uint8_t*>(src->data.data());
+  if (src->encoding == "bgr8") {
+    out->image = cv::Mat(h, w, CV_8UC3, base, src->step);
+    return out;
+  }
+  int bpp, ib, ig, ir;
+  if (src->encoding == "rgb8") { bpp = 3; ib = 2; ig = 1; ir = 0; }
+  else if (src->encoding == "bgra8") { bpp = 4; ib = 0; ig = 1; ir = 2; }
+  else if (src->encoding == "rgba8") { bpp = 4; ib = 2; ig = 1; ir = 0; }
+  else if (src->encoding == "mono8") { bpp = 1; ib = 0; ig = 0; ir = 0; }
+  else throw std::runtime_error("ref_shim: unsupported source encoding " + src->encoding);
+  out->image.create(h, w, CV_8UC3);
+  for (int r = 0; r < h; r++)
+    for (int c = 0; c < w; c++) {
+      const uint8_t* p = base + (size_t)r * src->step + (size_t)c * bpp;
+      out->image.at<cv::Vec3b>(r, c) = cv::Vec3b(p[ib], p[ig], p[ir]);
+    }
+  return out;
+}
 }  // namespace cv_bridge
 
 // ------------------------------------------------------------------------------- image_transport, message_filters
 namespace image_transport {
 class Publisher : public ros::Publisher {};
+struct CameraPubState { int n_published = 0; sensor_msgs::Image image; sensor_msgs::CameraInfo info; };
+class CameraPublisher {
+ public:
+  std::shared_ptr<CameraPubState> state;
+  void publish(const sensor_msgs::Image& image, const sensor_msgs::CameraInfo& info) const {
+    if (state) { state->image = image; state->info = info; state->n_published++; }
+  }
+};
+class CameraSubscriber {};
 class ImageTransport {
  public:
   explicit ImageTransport(const ros::NodeHandle&) {}
   Publisher advertise(const std::string& topic, uint32_t) {
     Publisher p; p.state = std::make_shared<ros::PubState>(); p.state->topic = topic; return p;
   }
+  CameraPublisher advertiseCamera(const std::string&, uint32_t);
+  template <class T>
+  CameraSubscriber subscribeCamera(const std::string&, uint32_t,
+                                   void (T::*)(const sensor_msgs::ImageConstPtr&, const sensor_msgs::CameraInfoConstPtr&), T*);
 };
 class SubscriberFilter {
  public:
   void subscribe(ImageTransport&, const std::string&, uint32_t) {}
 };
+
+inline CameraPublisher ImageTransport::advertiseCamera(const std::string&, uint32_t) {
+  CameraPublisher p; p.state = std::make_shared<CameraPubState>(); return p;
+}
+template <class T>
+CameraSubscriber ImageTransport::subscribeCamera(const std::string&, uint32_t,
+                                                 void (T::*)(const sensor_msgs::ImageConstPtr&,
+                                                             const sensor_msgs::CameraInfoConstPtr&), T*) {
+  return CameraSubscriber();
+}
 inline std::string getCameraInfoTopic(const std::string& base) { return base + "/camera_info"; }
 }  // namespace image_transport
 namespace message_filters {
