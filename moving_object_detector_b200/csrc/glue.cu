@@ -4,8 +4,9 @@
 // crops the camera image to target_width x target_height around the image centre after cv_bridge::toCvShare(msg,
 // "bgr8") (a channel shuffle for rgb8 / bgra8 / rgba8 / mono8 sources) and shifts the principal point of the
 // CameraInfo.  On the GPU it is one pass: every thread produces four output pixels (12 bytes, three aligned 32-bit
-// stores) of the dense bgr8 result from their source bytes; reads of neighbouring threads are contiguous, so both
-// sides move whole sectors.  Pure byte moves: HBM-bound, bit-exact by construction.
+// stores) of the dense bgr8 result; reads of neighbouring threads are contiguous, so both sides move whole sectors.
+// Two kernels: word loads + funnel shift + byte permute when a thread's four pixels share a row (target_w % 4 == 0),
+// a byte-wise kernel otherwise.  Pure byte moves: HBM-bound, bit-exact by construction.
 #include "common.cuh"
 
 namespace mod {
@@ -65,6 +66,50 @@ __global__ void __launch_bounds__(256) image_crop_kernel(const CropParams p) {
   }
 }
 
+// Fast path (target_w % 4 == 0, 4-byte aligned output): a thread's four pixels lie in one row, so their source bytes are
+// one contiguous run of 4 * kBpp bytes.  The run is fetched as aligned 32-bit words (one more than kBpp when it starts
+// inside a word) and shifted into place with funnel shifts; the channel shuffle of the encoding is then a fixed byte
+// permutation (PRMT) into three output words.  ~3x fewer instructions than the byte-wise kernel.
+template <int kBpp, int kB, int kG, int kR>
+__global__ void __launch_bounds__(256) image_crop_rows_kernel(const CropParams p) {
+  const int groups_per_row = p.tw >> 2;
+  const size_t groups = static_cast<size_t>(groups_per_row) * p.th * p.batch;
+  for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < groups;
+       g += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = g / groups_per_row;  // frame * th + r
+    const int c = static_cast<int>(g - row * groups_per_row) << 2;
+    const size_t frame = row / p.th;
+    const int r = static_cast<int>(row - frame * p.th);
+    const uint8_t* s = p.src + frame * p.src_frame_stride + static_cast<size_t>(p.y0 + r) * p.step +
+                       static_cast<size_t>(p.x0 + c) * kBpp;
+    const unsigned shift = static_cast<unsigned>(reinterpret_cast<uintptr_t>(s) & 3u);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s - shift);
+    uint32_t wsrc[kBpp + 1], a[kBpp];
+#pragma unroll
+    for (int k = 0; k < kBpp; k++) wsrc[k] = __ldg(wp + k);
+    wsrc[kBpp] = shift ? __ldg(wp + kBpp) : 0u;  // only touched when the run really extends into it
+#pragma unroll
+    for (int k = 0; k < kBpp; k++) a[k] = __funnelshift_r(wsrc[k], wsrc[k + 1], 8 * shift);
+    // output byte j = 3 * pixel + channel comes from source byte pixel * kBpp + {kB, kG, kR}[channel]
+    uint32_t o[3];
+#pragma unroll
+    for (int wd = 0; wd < 3; wd++) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int j = 4 * wd + b, px = j / 3, ch = j - 3 * px;
+        const int sb = px * kBpp + (ch == 0 ? kB : (ch == 1 ? kG : kR));
+        v |= ((a[sb >> 2] >> (8 * (sb & 3))) & 0xffu) << (8 * b);
+      }
+      o[wd] = v;
+    }
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(p.out + (row * p.tw + c) * 3);
+    o32[0] = o[0];
+    o32[1] = o[1];
+    o32[2] = o[2];
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_image_crop(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding,
@@ -77,7 +122,18 @@ cudaError_t launch_image_crop(cudaStream_t s, const uint8_t* src, size_t src_fra
                idx_of[encoding][0], idx_of[encoding][1], idx_of[encoding][2]};
   size_t blocks = ((total + 3) / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride beyond 16 CTAs per SM
-  image_crop_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+  const unsigned nb = static_cast<unsigned>(blocks);
+  if (tw % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    switch (encoding) {
+      case 0: image_crop_rows_kernel<3, 0, 1, 2><<<nb, 256, 0, s>>>(p); break;  // bgr8
+      case 1: image_crop_rows_kernel<3, 2, 1, 0><<<nb, 256, 0, s>>>(p); break;  // rgb8
+      case 2: image_crop_rows_kernel<4, 0, 1, 2><<<nb, 256, 0, s>>>(p); break;  // bgra8
+      case 3: image_crop_rows_kernel<4, 2, 1, 0><<<nb, 256, 0, s>>>(p); break;  // rgba8
+      default: image_crop_rows_kernel<1, 0, 0, 0><<<nb, 256, 0, s>>>(p); break; // mono8
+    }
+    return cudaGetLastError();
+  }
+  image_crop_kernel<<<nb, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 
