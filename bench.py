@@ -207,7 +207,7 @@ def main_reference(args):
         "gpu_launches": 0,
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -461,13 +461,33 @@ def main_ours(args):
             "objects_per_step": n_objects, "frames_with_error_status": bad,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
     return 0
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its version line with a
+    plain printf, whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    claim_stdout()
     a = parse_args()
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
