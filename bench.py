@@ -280,10 +280,16 @@ def main_ours(args):
                                seq["min_disparity"], seq["max_disparity"])
     points = torch.empty((B, P, 8), dtype=torch.float32, device=dev)
     mask = torch.empty((B, P), dtype=torch.uint8, device=dev)
-    objs = torch.zeros((B, MAX_OBJS * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    from moving_object_detector_b200.sharding import gather_object_lists
-    gathered = None
+    gatherer = None
+    if world > 1:
+        # the only collective (per-frame object lists, never pixel data): one all-gather per step on a
+        # side stream, overlapped by the next step's scene-flow kernel, its buffers allocated once
+        from moving_object_detector_b200.sharding import ObjectListGatherer
+        gatherer = ObjectListGatherer(B, MAX_OBJS * OBJECT_DTYPE.itemsize, STATS_DTYPE.itemsize, dev)
+        objs, stats = gatherer.objs, gatherer.stats
+    else:
+        objs = torch.zeros((B, MAX_OBJS * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     sf_events = []
@@ -296,12 +302,15 @@ def main_ours(args):
         if record_sf:
             e1.record()
             sf_events.append((e0, e1))
+        if gatherer is not None:
+            gatherer.wait()  # the previous step's all-gather still reads objs / stats
         ctx.cluster_batched_dev(W, H, B, points, mask, cl_cfg, objs, stats, MAX_OBJS, stream=stream)
-        if world > 1:  # the only collective: per-frame object lists (never pixel data), SURVEY.md 8(e)
-            nonlocal gathered
-            gathered = gather_object_lists(objs, stats)
+        if gatherer is not None:
+            gatherer.launch()
 
     def barrier():
+        if gatherer is not None:
+            gatherer.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -320,6 +329,8 @@ def main_ours(args):
     t_start.record()
     for _ in range(args.steps):
         step(True)
+    if gatherer is not None:
+        gatherer.wait()  # the last step's all-gather is inside the timed region
     t_end.record()
     barrier()
     launches = ctx.launch_count - launches0

@@ -49,6 +49,62 @@ def gather_object_lists(objs, stats, group=None):
     return g_objs.view((world,) + tuple(objs.shape)), g_stats.view((world,) + tuple(stats.shape))
 
 
+class ObjectListGatherer:
+    """The per-step collective of the data-parallel path with its buffers allocated once.
+
+    `objs` (block, objs_bytes) and `stats` (block, stats_bytes) are uint8 views into ONE flat send buffer, so that a
+    single all-gather moves both; the clusterer writes into them through their device pointers.  On CUDA the
+    collective runs on a side stream: launch() orders it after everything already enqueued on the current stream,
+    the next step's scene-flow kernel overlaps it, and wait() must be called (on the current stream) before the send
+    buffers are overwritten and before results are read.  On CPU tensors (gloo, tests) everything is synchronous.
+    """
+
+    def __init__(self, block: int, objs_bytes: int, stats_bytes: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.block, self.objs_bytes, self.stats_bytes = block, objs_bytes, stats_bytes
+        n = block * (objs_bytes + stats_bytes)
+        self._send = torch.zeros(n, dtype=torch.uint8, device=device)
+        self._recv = torch.zeros(self.world * n, dtype=torch.uint8, device=device)
+        self.objs = self._send[:block * objs_bytes].view(block, objs_bytes)
+        self.stats = self._send[block * objs_bytes:].view(block, stats_bytes)
+        self._cuda = self._send.is_cuda
+        if self._cuda:
+            self._side = torch.cuda.Stream(device=device)
+            self._ready = torch.cuda.Event()
+            self._done = torch.cuda.Event()
+        self._pending = False
+
+    def launch(self):
+        import torch
+        import torch.distributed as dist
+        if not self._cuda:
+            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            return
+        self._ready.record()
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ready)
+            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            self._done.record()
+        self._pending = True
+
+    def wait(self):
+        """Makes the current stream wait for the collective launched last (no host synchronisation)."""
+        import torch
+        if self._cuda and self._pending:
+            torch.cuda.current_stream().wait_event(self._done)
+            self._pending = False
+
+    def result(self):
+        """(world, block, objs_bytes) and (world, block, stats_bytes) views of the gathered buffer; call wait() first."""
+        per = self._recv.view(self.world, -1)
+        split = self.block * self.objs_bytes
+        return (per[:, :split].reshape(self.world, self.block, self.objs_bytes),
+                per[:, split:].reshape(self.world, self.block, self.stats_bytes))
+
+
 def merge_gathered(g_objs: np.ndarray, g_stats: np.ndarray, n_pairs: int, obj_dtype, stats_dtype) -> List[np.ndarray]:
     """Host side of the gather: per-pair object arrays in global pair order (drops the padding rows)."""
     world = g_objs.shape[0]

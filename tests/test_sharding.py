@@ -76,6 +76,17 @@ def _worker(rank, world, port, n_pairs, q):
         for g, rec in enumerate(merged):
             ok &= len(rec) == g % 3
             ok &= all(int(r["n_points"]) == 100 + g and float(r["center"][0]) == g for r in rec)
+        # the benchmark's form of the same exchange: one all-gather of a preallocated flat buffer, two steps in a row
+        from moving_object_detector_b200.sharding import ObjectListGatherer
+        gat = ObjectListGatherer(t_objs.shape[0], t_objs.shape[1], t_stats.shape[1], "cpu")
+        for step in range(2):
+            gat.wait()
+            gat.objs.copy_(t_objs)
+            gat.stats.copy_(t_stats)
+            gat.launch()
+        gat.wait()
+        o2, s2 = gat.result()
+        ok &= bool(torch.equal(o2, g_objs) and torch.equal(s2, g_stats))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
