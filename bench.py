@@ -42,7 +42,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="zed_1280x720")
@@ -96,9 +96,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived between host times t0 and t1 (the timed region); all if None."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -108,7 +109,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for stamp, line in self.lines:
+            if t0 is not None and not (t0 <= stamp <= t1):
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -325,6 +328,7 @@ def main_ours(args):
         time.sleep(0.25)
     launches0 = ctx.launch_count
     barrier()
+    host_t0 = time.perf_counter()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):
@@ -333,14 +337,15 @@ def main_ours(args):
         gatherer.wait()  # the last step's all-gather is inside the timed region
     t_end.record()
     barrier()
+    host_t1 = time.perf_counter()
     launches = ctx.launch_count - launches0
     elapsed_ms = t_start.elapsed_time(t_end)
     sf_ms = [a.elapsed_time(b) for a, b in sf_events]
-    # a longer burst of scene-flow launches alone gives the sampler something to see and a second roofline figure
     clocks = None
     if rank == 0:
-        time.sleep(0.15)
-        clocks = sampler.stop()
+        time.sleep(0.1)
+        # nvidia-smi reports every 50 ms; a sample arriving up to one period after the region still describes it
+        clocks = sampler.stop(host_t0 + 0.02, host_t1 + 0.06)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
