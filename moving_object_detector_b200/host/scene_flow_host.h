@@ -21,13 +21,21 @@
 #include "../../include/mod_b200.h"
 #include "ros_compat.h"
 
+#ifdef MOD_HAVE_ROS
+// the dynamic_reconfigure-generated parameter structs (cfg/SceneFlowConstructor.cfg, cfg/Clusterer.cfg)
+#include <scene_flow_clusterer/ClustererConfig.h>
+#include <scene_flow_constructor/SceneFlowConstructorConfig.h>
+#endif
+
 namespace scene_flow_constructor {
 
+#ifndef MOD_HAVE_ROS
 // cfg/SceneFlowConstructor.cfg:8-9 (generated SceneFlowConstructorConfig has exactly these two members)
 struct SceneFlowConstructorConfig {
   int dynamic_flow_diff = 5;
   double max_color_velocity = 1.0;
 };
+#endif
 
 template <typename Msg>
 struct Sink {  // ros::Publisher stand-in: publish() + getNumSubscribers()
@@ -89,6 +97,7 @@ void describeVelocityCloud(sensor_msgs::PointCloud2& msg, uint32_t width, uint32
 
 namespace scene_flow_clusterer {
 
+#ifndef MOD_HAVE_ROS
 // cfg/Clusterer.cfg:8-11
 struct ClustererConfig {
   int cluster_size = 2500;
@@ -96,6 +105,7 @@ struct ClustererConfig {
   double dynamic_speed = 0.3;
   int neighbor_distance = 4;
 };
+#endif
 
 // pcl::fromROSMsg<pcl::PointXYZVelocity> equivalents (clusterer_nodelet.cpp:226).  velocityCloudLayout: 1 = the
 // constructor's own layout (32-byte records, dense rows: usable in place), 0 = another layout that carries the fields

@@ -4,7 +4,7 @@
 //
 // TEST INFRASTRUCTURE ONLY.  None of ROS Melodic / PCL 1.8 / Eigen 3.3 / OpenCV 3.2 is installed in this image, so the
 // reference cannot be built as shipped.  With this header on the include path (oracle/Makefile writes one forwarding
-// header per <path/name.h> the reference includes into oracle/_ref/include/), the reference's OWN sources
+// header per <path/name.h> the reference includes into oracle/_shim/include/), the reference's OWN sources
 //   disparity_image_proc/src/disparity_image_processor.cpp
 //   scene_flow_constructor/src/scene_flow_constructor.cpp
 //   scene_flow_clusterer/src/{clusterer_nodelet,color_set,lookup_table}.cpp
@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <any>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -60,6 +61,10 @@ using namespace std::placeholders;  // boost/bind.hpp puts _1, _2 ... in the glo
 #define NODELET_INFO(...) MOD_REF_NOLOG()
 #define NODELET_INFO_STREAM(x) MOD_REF_NOLOG()
 #define NODELET_DEBUG(...) MOD_REF_NOLOG()
+#define NODELET_WARN(...) MOD_REF_NOLOG()
+#define NODELET_ERROR(...) MOD_REF_NOLOG()
+#define NODELET_ERROR_STREAM(x) MOD_REF_NOLOG()
+#define NODELET_WARN_STREAM(x) MOD_REF_NOLOG()
 #define PLUGINLIB_EXPORT_CLASS(cls, base)
 
 // ------------------------------------------------------------------------------------------------------- rostime
@@ -115,7 +120,8 @@ struct CameraInfo {
   uint32_t height = 0, width = 0;
   std::string distortion_model;
   std::vector<double> D;
-  double K[9] = {0}, R[9] = {0}, P[12] = {0};
+  std::array<double, 9> K{}, R{};   // boost::array in ROS: operator[], data(), size()
+  std::array<double, 12> P{};
   uint32_t binning_x = 0, binning_y = 0;
   RegionOfInterest roi;
 };
