@@ -22,6 +22,8 @@
 #include <sensor_msgs/PointCloud2.h>
 #include <visualization_msgs/MarkerArray.h>
 
+#include "msg_describe.h"
+
 namespace cv {
 const uchar*& mod_ref_colormap_table() {
   static const uchar* table = nullptr;
@@ -50,6 +52,7 @@ sensor_msgs::CameraInfo make_camera_info(int w, int h, const ref_camera& c) {
 stereo_msgs::DisparityImage make_disparity_msg(int w, int h, const ref_disparity& d, uint32_t sec, uint32_t nsec) {
   stereo_msgs::DisparityImage m;
   m.header.stamp = ros::Time(sec, nsec);
+  m.header.frame_id = "disparity_frame";
   m.image.width = w; m.image.height = h; m.image.encoding = "32FC1";
   m.image.step = (uint32_t)d.step_bytes;
   m.image.data.resize((size_t)d.step_bytes * h);
@@ -67,6 +70,7 @@ void prime_constructor(scene_flow_constructor::SceneFlowConstructor& node, int w
   node.left_cam_model_->fromCameraInfo(info);
   node.image_width_ = w;
   node.image_height_ = h;
+  node.camera_frame_id_ = "left_camera_optical";  // left_image->header.frame_id (:373)
   scene_flow_constructor::SceneFlowConstructorConfig cfg;
   cfg.dynamic_flow_diff = dynamic_flow_diff;
   node.reconfigureCB(cfg, 0);
@@ -76,8 +80,11 @@ void prime_constructor(scene_flow_constructor::SceneFlowConstructor& node, int w
   node.optflow_pub_.state->num_subscribers = (subscribers & 8) ? 1 : 0;
 }
 
-std::shared_ptr<cv_bridge::CvImage> make_flow(int w, int h, const float* flow_xy, int32_t flow_step_bytes) {
-  std::shared_ptr<cv_bridge::CvImage> flow(new cv_bridge::CvImage(std_msgs::Header(), sensor_msgs::image_encodings::TYPE_32FC2));
+std::shared_ptr<cv_bridge::CvImage> make_flow(int w, int h, const float* flow_xy, int32_t flow_step_bytes,
+                                              uint32_t sec = 0, uint32_t nsec = 0) {
+  std_msgs::Header hd;  // estimateOpticalFlow stamps the flow with the left image's header (:281)
+  hd.seq = 42; hd.stamp = ros::Time(sec + 1, nsec); hd.frame_id = "flow_frame";  // distinct from the disparity header on purpose
+  std::shared_ptr<cv_bridge::CvImage> flow(new cv_bridge::CvImage(hd, sensor_msgs::image_encodings::TYPE_32FC2));
   flow->image = cv::Mat(h, w, CV_32FC2, (void*)flow_xy, (size_t)flow_step_bytes);  // pwc_net fills a cv::Mat of this type
   return flow;
 }
@@ -117,6 +124,8 @@ void prime_clusterer(scene_flow_clusterer::ClustererNodelet& node, int32_t clust
 
 // the last ~scene_flow message, so that a test can feed the clusterer the very message the constructor published
 sensor_msgs::PointCloud2Ptr g_last_cloud;
+// metadata of everything the last ref_scene_flow call published (oracle/msg_describe.h)
+std::string g_last_description;
 
 }  // namespace
 
@@ -161,16 +170,18 @@ int ref_scene_flow(int w, int h, const ref_camera* cam, const ref_disparity* now
     if (now) dnow.reset(new DisparityImageProcessor(make_disparity_msg(w, h, *now, now_sec, now_nsec), info));
     if (prev) dprev.reset(new DisparityImageProcessor(make_disparity_msg(w, h, *prev, prev_sec, prev_nsec), info));
     std::shared_ptr<cv_bridge::CvImage> flow;
-    if (flow_xy) flow = make_flow(w, h, flow_xy, flow_step_bytes);
+    if (flow_xy) flow = make_flow(w, h, flow_xy, flow_step_bytes, now_sec, now_nsec);
     geometry_msgs::TransformPtr tf;
     if (prev2now) tf = make_transform(*prev2now);
 
     node.construct(dnow, dprev, flow, tf);
 
     int pub = 0;
+    std::vector<std::pair<long, std::string>> described;  // (publication order, description)
     if (node.pc_with_velocity_pub_.state->n_published) {
       pub |= 1;
       const sensor_msgs::PointCloud2& m = *std::any_cast<sensor_msgs::PointCloud2>(&node.pc_with_velocity_pub_.state->last);
+      described.emplace_back(node.pc_with_velocity_pub_.state->order, mod_describe::cloud("scene_flow", m));
       g_last_cloud.reset(new sensor_msgs::PointCloud2(m));
       if (out_points32) std::memcpy(out_points32, m.data.data(), std::min(m.data.size(), (size_t)w * h * 32));
       if (cloud_meta) {
@@ -188,18 +199,24 @@ int ref_scene_flow(int w, int h, const ref_camera* cam, const ref_disparity* now
     if (node.depth_pub_.state->n_published) {
       pub |= 2;
       const sensor_msgs::Image& m = *std::any_cast<sensor_msgs::Image>(&node.depth_pub_.state->last);
+      described.emplace_back(node.depth_pub_.state->order, mod_describe::image("depth", m));
       if (out_depth) std::memcpy(out_depth, m.data.data(), std::min(m.data.size(), (size_t)w * h * 4));
     }
     if (node.static_flow_pub_.state->n_published) {
       pub |= 4;
       const sensor_msgs::Image& m = *std::any_cast<sensor_msgs::Image>(&node.static_flow_pub_.state->last);
+      described.emplace_back(node.static_flow_pub_.state->order, mod_describe::image("synthetic_optical_flow", m));
       if (out_static_flow) std::memcpy(out_static_flow, m.data.data(), std::min(m.data.size(), (size_t)w * h * 8));
     }
     if (node.optflow_pub_.state->n_published) {
       pub |= 8;
       const sensor_msgs::Image& m = *std::any_cast<sensor_msgs::Image>(&node.optflow_pub_.state->last);
+      described.emplace_back(node.optflow_pub_.state->order, mod_describe::image("optical_flow", m));
       if (out_flow_echo) std::memcpy(out_flow_echo, m.data.data(), std::min(m.data.size(), (size_t)w * h * 8));
     }
+    std::sort(described.begin(), described.end());
+    g_last_description.clear();
+    for (const auto& d : described) g_last_description += d.second;
     if (published) *published = pub;
     return 0;
   } catch (const std::out_of_range&) {
@@ -207,6 +224,13 @@ int ref_scene_flow(int w, int h, const ref_camera* cam, const ref_disparity* now
   } catch (...) {
     return -11;
   }
+}
+
+/* metadata (header, layout, encoding; not the payload) of the messages the last ref_scene_flow call published */
+int ref_last_description(char* buf, int cap) {
+  if (!buf || cap <= 0) return -1;
+  std::snprintf(buf, (size_t)cap, "%s", g_last_description.c_str());
+  return (int)g_last_description.size();
 }
 
 /*

@@ -90,8 +90,10 @@ def scene_flow(disp_now, disp_prev, flow, cam, transform, stamp_prev, stamp_now,
                             C.c_uint32(stamp_prev[0]), C.c_uint32(stamp_prev[1]), C.c_uint32(stamp_now[0]),
                             C.c_uint32(stamp_now[1]), C.c_int32(dynamic_flow_diff), C.c_int(subscribers), p(out),
                             p(depth), p(static), p(echo), C.byref(pub), p(meta))
+    buf = C.create_string_buffer(4096)
+    lib.ref_last_description(buf, 4096)
     return dict(status=rc, published=pub.value, points32=out, depth=depth, static_flow=static, flow_echo=echo,
-                cloud_meta=meta)
+                cloud_meta=meta, description=buf.value.decode())
 
 
 def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=4, max_objs=4096,

@@ -206,14 +206,17 @@ struct MovingObjectArray { std_msgs::Header header; std::vector<MovingObject> mo
 
 // ------------------------------------------------------------------------------------------------------- roscpp
 namespace ros {
-struct PubState { std::string topic; int num_subscribers = 0; int n_published = 0; std::any last; };
+inline long& mod_ref_publish_counter() { static thread_local long n = 0; return n; }  // orders publications across topics
+struct PubState { std::string topic; int num_subscribers = 0; int n_published = 0; long order = 0; std::any last; };
 class Publisher {
  public:
   std::shared_ptr<PubState> state;
   uint32_t getNumSubscribers() const { return state ? (uint32_t)state->num_subscribers : 0u; }
-  template <class M> void publish(const M& msg) const { if (state) { state->last = msg; state->n_published++; } }
+  template <class M> void publish(const M& msg) const {
+    if (state) { state->last = msg; state->n_published++; state->order = ++mod_ref_publish_counter(); }
+  }
   template <class M> void publish(const std::shared_ptr<M>& msg) const {
-    if (state) { state->last = typename std::remove_const<M>::type(*msg); state->n_published++; }
+    if (state) { state->last = typename std::remove_const<M>::type(*msg); state->n_published++; state->order = ++mod_ref_publish_counter(); }
   }
 };
 class Subscriber {};

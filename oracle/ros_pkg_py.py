@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from oracle_py import OBJECT_DTYPE
+from oracle_py import OBJECT_DTYPE, Transform, _cam, _disp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_shim", "libclusterer_nodelet_b200.so")
@@ -25,6 +25,7 @@ def load():
         _lib = C.CDLL(LIB_PATH)
         _lib.rosb200_defaults.restype = C.c_int
         _lib.rosb200_cluster.restype = C.c_int
+        _lib.rosb200_scene_flow.restype = C.c_int
     return _lib
 
 
@@ -34,6 +35,32 @@ def defaults():
     d2 = (C.c_double * 2)()
     assert lib.rosb200_defaults(i3, d2) == 0
     return dict(cluster_size=i3[0], neighbor_distance=i3[1], topics_ok=i3[2], depth_diff=d2[0], dynamic_speed=d2[1])
+
+
+def scene_flow(disp_now, disp_prev, flow, cam, transform, stamp_prev, stamp_now, dynamic_flow_diff=5, f=1.0, T=1.0,
+               min_disparity=0.0, max_disparity=128.0, subscribers=7):
+    """SceneFlowConstructorB200::construct on one pair; arguments and result keys as ref_py.scene_flow."""
+    lib = load()
+    ref_img = disp_now if disp_now is not None else disp_prev
+    h, w = ref_img.shape if ref_img is not None else flow.shape[:2]
+    out = np.full((h, w, 8), -12345.0, np.float32)
+    depth = np.full((h, w), -12345.0, np.float32)
+    static = np.full((h, w, 2), -12345.0, np.float32)
+    echo = np.full((h, w, 2), -12345.0, np.float32)
+    pub = C.c_int32(0)
+    c = _cam(cam)
+    dn = _disp(disp_now, f, T, min_disparity, max_disparity) if disp_now is not None else None
+    dp = _disp(disp_prev, f, T, min_disparity, max_disparity) if disp_prev is not None else None
+    t = Transform(*[float(v) for v in transform]) if transform is not None else None
+    p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    buf = C.create_string_buffer(4096)
+    rc = lib.rosb200_scene_flow(w, h, C.byref(c), C.byref(dn) if dn else None, C.byref(dp) if dp else None, p(flow),
+                                C.c_int32(flow.strides[0] if flow is not None else 0), C.byref(t) if t else None,
+                                C.c_uint32(stamp_prev[0]), C.c_uint32(stamp_prev[1]), C.c_uint32(stamp_now[0]),
+                                C.c_uint32(stamp_now[1]), C.c_int32(dynamic_flow_diff), C.c_int(subscribers), p(out),
+                                p(depth), p(static), p(echo), C.byref(pub), buf, 4096)
+    return dict(status=rc, published=pub.value, points32=out, depth=depth, static_flow=static, flow_echo=echo,
+                description=buf.value.decode())
 
 
 def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=4, max_objs=4096,

@@ -13,6 +13,8 @@
 #include "clusterer_nodelet_b200.h"
 #include <visualization_msgs/MarkerArray.h>
 
+#include "msg_describe.h"
+
 namespace {
 sensor_msgs::PointCloud2Ptr make_cloud_msg(int w, int h, const void* points32) {
   sensor_msgs::PointCloud2Ptr m(new sensor_msgs::PointCloud2());
@@ -31,7 +33,94 @@ sensor_msgs::PointCloud2Ptr make_cloud_msg(int w, int h, const void* points32) {
 }
 }  // namespace
 
+struct rb_camera { double fx, fy, cx, cy, Tx, Ty; };
+struct rb_disparity { float f, T, min_disparity, max_disparity; const float* data; int32_t step_bytes; };
+struct rb_transform { double tx, ty, tz, qx, qy, qz, qw; };
+
+static std::shared_ptr<stereo_msgs::DisparityImage> rb_disparity_msg(int w, int h, const rb_disparity& d, uint32_t sec,
+                                                                       uint32_t nsec) {
+  auto m = std::make_shared<stereo_msgs::DisparityImage>();
+  m->header.stamp = ros::Time(sec, nsec);
+  m->header.frame_id = "disparity_frame";
+  m->image.width = w; m->image.height = h; m->image.encoding = "32FC1"; m->image.step = (uint32_t)d.step_bytes;
+  m->image.data.resize((size_t)d.step_bytes * h);
+  for (int r = 0; r < h; r++)
+    std::memcpy(&m->image.data[(size_t)r * d.step_bytes], (const char*)d.data + (size_t)r * d.step_bytes, (size_t)w * 4);
+  m->f = d.f; m->T = d.T; m->min_disparity = d.min_disparity; m->max_disparity = d.max_disparity;
+  return m;
+}
+
 extern "C" {
+
+/*
+ * SceneFlowConstructorB200::construct (the product's stand-in for SceneFlowConstructor::construct) on one frame pair,
+ * with the argument meaning of ref_scene_flow (oracle/ref_full_wrap.cpp).  description receives the metadata of the
+ * published messages in the format of oracle/msg_describe.h.
+ */
+int rosb200_scene_flow(int w, int h, const rb_camera* cam, const rb_disparity* now, const rb_disparity* prev,
+                       const float* flow_xy, int32_t flow_step_bytes, const rb_transform* prev2now, uint32_t prev_sec,
+                       uint32_t prev_nsec, uint32_t now_sec, uint32_t now_nsec, int32_t dynamic_flow_diff,
+                       int subscribers, void* out_points32, float* out_depth, float* out_static_flow,
+                       float* out_flow_echo, int32_t* published, char* description, int description_cap) {
+  try {
+    namespace sfc = scene_flow_constructor;
+    sfc::SceneFlowConstructorB200 node(w, h);
+    sfc::SceneFlowConstructorConfig cfg;
+    cfg.dynamic_flow_diff = dynamic_flow_diff;
+    node.reconfigureCB(cfg, 0);
+    sensor_msgs::CameraInfo info;
+    info.header.frame_id = "left_camera_optical";
+    info.width = w; info.height = h;
+    info.P[0] = cam->fx; info.P[2] = cam->cx; info.P[3] = cam->Tx;
+    info.P[5] = cam->fy; info.P[6] = cam->cy; info.P[7] = cam->Ty; info.P[10] = 1.0;
+    node.setCameraInfo(info);
+    std::string desc;
+    int pub = 0;
+    const size_t P = (size_t)w * h;
+    node.pc_with_velocity_pub_ = {[&](const sensor_msgs::PointCloud2& m) {
+      pub |= 1; desc += mod_describe::cloud("scene_flow", m);
+      if (out_points32) std::memcpy(out_points32, m.data.data(), std::min(m.data.size(), P * 32));
+    }, (subscribers & 1) ? 1 : 0};
+    node.depth_pub_ = {[&](const sensor_msgs::Image& m) {
+      pub |= 2; desc += mod_describe::image("depth", m);
+      if (out_depth) std::memcpy(out_depth, m.data.data(), std::min(m.data.size(), P * 4));
+    }, (subscribers & 2) ? 1 : 0};
+    node.static_flow_pub_ = {[&](const sensor_msgs::Image& m) {
+      pub |= 4; desc += mod_describe::image("synthetic_optical_flow", m);
+      if (out_static_flow) std::memcpy(out_static_flow, m.data.data(), std::min(m.data.size(), P * 8));
+    }, (subscribers & 4) ? 1 : 0};
+    node.optflow_pub_ = {[&](const sensor_msgs::Image& m) {
+      pub |= 8; desc += mod_describe::image("optical_flow", m);
+      if (out_flow_echo) {
+        for (int r = 0; r < h; r++) std::memcpy((char*)out_flow_echo + (size_t)r * w * 8, &m.data[(size_t)r * m.step], (size_t)w * 8);
+      }
+    }, (subscribers & 8) ? 1 : 0};
+
+    std::shared_ptr<stereo_msgs::DisparityImage> dnow, dprev;
+    if (now) dnow = rb_disparity_msg(w, h, *now, now_sec, now_nsec);
+    if (prev) dprev = rb_disparity_msg(w, h, *prev, prev_sec, prev_nsec);
+    std::shared_ptr<sensor_msgs::Image> flow;
+    if (flow_xy) {
+      flow = std::make_shared<sensor_msgs::Image>();
+      flow->header.seq = 42; flow->header.stamp = ros::Time(now_sec + 1, now_nsec); flow->header.frame_id = "flow_frame";
+      flow->width = w; flow->height = h; flow->encoding = "32FC2"; flow->step = (uint32_t)w * 8;  // cv_bridge emits dense rows
+      flow->data.resize(P * 8);
+      for (int r = 0; r < h; r++) std::memcpy(&flow->data[(size_t)r * w * 8], (const char*)flow_xy + (size_t)r * flow_step_bytes, (size_t)w * 8);
+    }
+    std::shared_ptr<geometry_msgs::Transform> tf;
+    if (prev2now) {
+      tf = std::make_shared<geometry_msgs::Transform>();
+      tf->translation.x = prev2now->tx; tf->translation.y = prev2now->ty; tf->translation.z = prev2now->tz;
+      tf->rotation.x = prev2now->qx; tf->rotation.y = prev2now->qy; tf->rotation.z = prev2now->qz; tf->rotation.w = prev2now->qw;
+    }
+    node.construct(dnow, dprev, flow, tf);
+    if (published) *published = pub;
+    if (description && description_cap > 0) std::snprintf(description, (size_t)description_cap, "%s", desc.c_str());
+    return node.lastError().empty() ? 0 : -13;
+  } catch (...) {
+    return -11;
+  }
+}
 
 /* topics the nodelet advertises and the defaults it latches at start-up: out3 = cluster_size, neighbor_distance,
  * n_topics_ok (3 when ~moving_objects, ~clusters, ~clusters_image are advertised under those names); out2d = depth_diff,

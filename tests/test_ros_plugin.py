@@ -123,3 +123,38 @@ def test_gpu_nodelet_on_a_constructor_cloud_and_subscriber_gating(plugin, oracle
     for subs in (0, 1, 2, 4, 5):
         r, q = plugin.cluster(cloud, subscribers=subs), ref_py.cluster(cloud, subscribers=subs)
         assert r["published"] & 7 == q["published"] & 7 == subs
+
+
+@pytest.mark.gpu
+def test_gpu_constructor_host_class_publishes_what_the_reference_node_publishes(plugin):
+    """SceneFlowConstructorB200::construct vs SceneFlowConstructor::construct at the ROS message level: payloads bit for
+    bit, and headers / layout / encodings / publication order of ~optical_flow, ~depth, ~scene_flow,
+    ~synthetic_optical_flow as strings (oracle/msg_describe.h), under the degrade rules and subscriber gates."""
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref/libmod_ref.so not in the snapshot")
+    from helpers import assert_cloud_bit_exact
+    from moving_object_detector_b200 import synth
+    seq = synth.make_sequence(synth.CONFIGS["gazebo_640x480"], 2)
+    disp, flows = seq["disp"].numpy(), seq["flows"].numpy()
+    now, prev, flow = (np.ascontiguousarray(a) for a in (disp[1], disp[0], flows[0]))
+    sp, sn, _ = ref_py.stamps_for(seq["dts"][0])
+    kw = dict(f=seq["f"], T=seq["T"], min_disparity=seq["min_disparity"], max_disparity=seq["max_disparity"])
+    tr = seq["transforms"][0]
+    fields = [0, 1, 2, 4, 5, 6]
+    cases = [(now, prev, flow, tr, 15), (now, prev, flow, tr, 1), (now, prev, flow, tr, 6), (now, prev, flow, tr, 0),
+             (now, prev, None, tr, 15), (now, None, flow, tr, 15), (now, prev, flow, None, 15), (None, prev, flow, tr, 15)]
+    for a_now, a_prev, a_flow, a_tr, subs in cases:
+        r = ref_py.scene_flow(a_now, a_prev, a_flow, seq["cam"], a_tr, sp, sn, subscribers=subs, **kw)
+        g = plugin.scene_flow(a_now, a_prev, a_flow, seq["cam"], a_tr, sp, sn, subscribers=subs, **kw)
+        assert r["status"] == 0 and g["status"] == 0
+        assert g["published"] == r["published"], (subs, g["published"], r["published"])
+        assert g["description"] == r["description"], f"message metadata / order differ:\n{g['description']}\n{r['description']}"
+        if r["published"] & 1:
+            assert_cloud_bit_exact(g["points32"][..., fields], r["points32"][..., fields], "~scene_flow")
+        if r["published"] & 2:
+            assert_cloud_bit_exact(g["depth"][..., None], r["depth"][..., None], "~depth")
+        if r["published"] & 4:
+            assert_cloud_bit_exact(g["static_flow"], r["static_flow"], "~synthetic_optical_flow")
+        if r["published"] & 8:
+            assert g["flow_echo"].tobytes() == r["flow_echo"].tobytes()   # the flow holds NaNs: compare bytes
