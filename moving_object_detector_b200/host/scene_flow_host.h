@@ -59,6 +59,9 @@ class SceneFlowConstructorB200 {
   // left CameraInfo as latched at scene_flow_constructor.cpp:368-374 (PinholeCameraModel::fromCameraInfo: binning
   // and ROI offsets are applied to P exactly as image_geometry does)
   void setCameraInfo(const sensor_msgs::CameraInfo& left_camera_info);
+  // frame_id the ~depth image is stamped with.  setCameraInfo takes it from the CameraInfo header; the reference node
+  // takes it from the first left image (:373) - a node that wants exactly that calls this afterwards.
+  void setCameraFrame(const std::string& frame_id) { camera_frame_id_ = frame_id; }
 
   // Same contract as SceneFlowConstructor::construct (:91-147): any argument may be null.
   //   ~optical_flow is published whenever left_flow is set and subscribed           (:99-100)

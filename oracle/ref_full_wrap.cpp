@@ -23,6 +23,7 @@
 #include <visualization_msgs/MarkerArray.h>
 
 #include "msg_describe.h"
+#include "node_sequence.h"
 
 namespace cv {
 const uchar*& mod_ref_colormap_table() {
@@ -413,6 +414,25 @@ int ref_bench_pipeline(int w, int h, const ref_camera* cam, float f, float T, fl
   if (best_sec) *best_sec = best;
   if (n_objects) *n_objects = objs_total.load();
   return failed ? -11 : 0;
+}
+
+/*
+ * The reference NODE driven through a sequence of stereo frames: SceneFlowConstructor::stereoCallback
+ * (scene_flow_constructor.cpp:364-399) once per frame, with the stand-in sgm_gpu / pwc_net / libviso2 replaying the
+ * given script, so that the frame-to-frame state (previous image / disparity, :397-398), the estimator-failure rules
+ * (:250-254, :270-276, :284-289), the odometry broadcast (:322-349) and construct() run exactly as written.  `log`
+ * receives every publication and tf broadcast in order (oracle/node_sequence.h).
+ */
+int ref_node_sequence(int w, int h, int n_frames, const mod_node_sequence::camera* cam, float f, float T, float min_d,
+                      float max_d, const float* disparities, const float* flows, const double* motions,
+                      const int32_t* ok_flags, const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff,
+                      char* log, int log_cap, int32_t* shutdown_requested) {
+  auto finish = [](scene_flow_constructor::SceneFlowConstructor& node) {
+    if (node.construct_thread_.joinable()) node.construct_thread_.join();
+  };
+  return mod_node_sequence::run<scene_flow_constructor::SceneFlowConstructor>(
+      w, h, n_frames, cam, f, T, min_d, max_d, disparities, flows, motions, ok_flags, stamps, subscribers,
+      dynamic_flow_diff, finish, log, log_cap, shutdown_requested);
 }
 
 }  // extern "C"

@@ -33,6 +33,7 @@
 #include <functional>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -52,6 +53,7 @@ using namespace std::placeholders;  // boost/bind.hpp puts _1, _2 ... in the glo
 #define ROS_INFO(...) MOD_REF_NOLOG()
 #define ROS_WARN(...) MOD_REF_NOLOG()
 #define ROS_ERROR(...) MOD_REF_NOLOG()
+#define ROS_FATAL(...) MOD_REF_NOLOG()
 #define ROS_DEBUG_STREAM(x) MOD_REF_NOLOG()
 #define ROS_INFO_STREAM(x) MOD_REF_NOLOG()
 #define ROS_WARN_STREAM(x) MOD_REF_NOLOG()
@@ -208,16 +210,27 @@ struct MovingObjectArray { std_msgs::Header header; std::vector<MovingObject> mo
 namespace ros {
 inline long& mod_ref_publish_counter() { static thread_local long n = 0; return n; }  // orders publications across topics
 struct PubState { std::string topic; int num_subscribers = 0; int n_published = 0; long order = 0; std::any last; };
+// Optional process-wide record of EVERYTHING that is published or broadcast on tf, in order and from whichever thread
+// (the constructor node publishes from a worker): a wrapper that drives a node through several frames installs one.
+struct PubEvent { std::string topic; std::any msg; };
+struct PubLog {
+  std::mutex mu;
+  std::vector<PubEvent> events;
+  void add(const std::string& topic, std::any msg) { std::lock_guard<std::mutex> l(mu); events.push_back(PubEvent{topic, std::move(msg)}); }
+};
+inline PubLog*& mod_ref_pub_log() { static PubLog* log = nullptr; return log; }
+inline bool& mod_ref_shutdown_requested() { static bool flag = false; return flag; }
+inline void shutdown() { mod_ref_shutdown_requested() = true; }
 class Publisher {
  public:
   std::shared_ptr<PubState> state;
   uint32_t getNumSubscribers() const { return state ? (uint32_t)state->num_subscribers : 0u; }
   template <class M> void publish(const M& msg) const {
-    if (state) { state->last = msg; state->n_published++; state->order = ++mod_ref_publish_counter(); }
+    if (!state) return;
+    state->last = msg; state->n_published++; state->order = ++mod_ref_publish_counter();
+    if (PubLog* log = mod_ref_pub_log()) log->add(state->topic, state->last);
   }
-  template <class M> void publish(const std::shared_ptr<M>& msg) const {
-    if (state) { state->last = typename std::remove_const<M>::type(*msg); state->n_published++; state->order = ++mod_ref_publish_counter(); }
-  }
+  template <class M> void publish(const std::shared_ptr<M>& msg) const { publish(typename std::remove_const<M>::type(*msg)); }
 };
 class Subscriber {};
 // integer parameters a test wants the nodes to find on the parameter server (image_crop's target_width / target_height)
@@ -428,7 +441,17 @@ class CvImage {
 };
 typedef std::shared_ptr<CvImage> CvImagePtr;
 typedef std::shared_ptr<const CvImage> CvImageConstPtr;
-inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr&, const std::string&) { return CvImagePtr(); }  // upstream glue, never run
+// cv_bridge::toCvCopy(msg, "mono8"): a deep copy when the source already is mono8.  Colour sources would go through
+// cv::cvtColor's fixed-point BGR2GRAY, which is not restated (it feeds libviso2, an upstream estimator): tests that drive
+// the constructor node through stereoCallback hand it mono8 images.
+inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr& src, const std::string& encoding) {
+  if (encoding != "mono8" || src->encoding != "mono8") throw std::runtime_error("ref_shim: toCvCopy only mono8 -> mono8");
+  CvImagePtr out = std::make_shared<CvImage>();
+  out->header = src->header;
+  out->encoding = encoding;
+  cv::Mat(src->height, src->width, CV_8UC1, const_cast<uint8_t*>(src->data.data()), src->step).copyTo(out->image);
+  return out;
+}
 // cv_bridge::toCvShare(msg, "bgr8") (cv_bridge/src/cv_bridge.cpp): shares the message's pixels when the encodings are
 // equal, otherwise converts with cv::cvtColor.  The colour conversions among 8-bit bgr8 / rgb8 / bgra8 / rgba8 / mono8
 // are pure channel shuffles (RGB2BGR swaps, BGRA2BGR drops alpha, GRAY2BGR replicates), restated here.
@@ -614,13 +637,50 @@ class Vector3 {
   double z() const { return m[2]; }
   double m[3] = {0, 0, 0};
 };
-// The tf2 classes below only appear in estimateCameraMotion / integrateAndBroadcastTF (odometry glue that is never
-// executed through this build); they exist so that those functions compile and link.
+// tf2 LinearMath (tf2/LinearMath/{Matrix3x3,Transform,Quaternion}.h), restated as far as estimateCameraMotion /
+// integrateAndBroadcastTF use it.  This is odometry glue AROUND the hot path: the reference node and the product node
+// both call these very functions, so a test that drives both through stereoCallback compares how they USE tf2, not tf2.
+//   Transform::inverse()      = (basis^T, basis^T * -origin)
+//   Transform * Transform     = (b1 * b2, b1 * o2 + o1);  operator*= likewise
+//   Matrix3x3::getRotation(q) = the trace / largest-diagonal branch of Matrix3x3.h
+//   toMsg(Transform)          = translation <- origin, rotation <- getRotation()
 class Matrix3x3 {
  public:
   Matrix3x3() {}
   Matrix3x3(double a, double b, double c, double d, double e, double f, double g, double h, double i) {
     m[0] = a; m[1] = b; m[2] = c; m[3] = d; m[4] = e; m[5] = f; m[6] = g; m[7] = h; m[8] = i;
+  }
+  double at(int r, int c) const { return m[3 * r + c]; }
+  Matrix3x3 transpose() const { return Matrix3x3(m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]); }
+  Matrix3x3 operator*(const Matrix3x3& o) const {
+    Matrix3x3 r;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) r.m[3 * i + j] = at(i, 0) * o.at(0, j) + at(i, 1) * o.at(1, j) + at(i, 2) * o.at(2, j);
+    return r;
+  }
+  Vector3 operator*(const Vector3& v) const {
+    return Vector3(m[0] * v.x() + m[1] * v.y() + m[2] * v.z(), m[3] * v.x() + m[4] * v.y() + m[5] * v.z(),
+                   m[6] * v.x() + m[7] * v.y() + m[8] * v.z());
+  }
+  void getRotation(double q[4]) const {  // q = x, y, z, w
+    const double trace = m[0] + m[4] + m[8];
+    if (trace > 0.0) {
+      double s = std::sqrt(trace + 1.0);
+      q[3] = s * 0.5;
+      s = 0.5 / s;
+      q[0] = (at(2, 1) - at(1, 2)) * s;
+      q[1] = (at(0, 2) - at(2, 0)) * s;
+      q[2] = (at(1, 0) - at(0, 1)) * s;
+    } else {
+      const int i = at(0, 0) < at(1, 1) ? (at(1, 1) < at(2, 2) ? 2 : 1) : (at(0, 0) < at(2, 2) ? 2 : 0);
+      const int j = (i + 1) % 3, k = (i + 2) % 3;
+      double s = std::sqrt(at(i, i) - at(j, j) - at(k, k) + 1.0);
+      q[i] = s * 0.5;
+      s = 0.5 / s;
+      q[3] = (at(k, j) - at(j, k)) * s;
+      q[j] = (at(j, i) + at(i, j)) * s;
+      q[k] = (at(k, i) + at(i, k)) * s;
+    }
   }
   double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 };
@@ -629,9 +689,15 @@ class Transform {
   Transform() {}
   Transform(const Matrix3x3& b, const Vector3& o) : basis(b), origin(o) {}
   void setIdentity() { basis = Matrix3x3(); origin = Vector3(); }
-  Transform inverse() const { return *this; }
-  Transform& operator*=(const Transform&) { return *this; }
-  Transform operator*(const Transform&) const { return *this; }
+  Transform inverse() const {
+    const Matrix3x3 inv = basis.transpose();
+    return Transform(inv, inv * Vector3(-origin.x(), -origin.y(), -origin.z()));
+  }
+  Transform operator*(const Transform& t) const {
+    const Vector3 o = basis * t.origin;
+    return Transform(basis * t.basis, Vector3(o.x() + origin.x(), o.y() + origin.y(), o.z() + origin.z()));
+  }
+  Transform& operator*=(const Transform& t) { *this = *this * t; return *this; }
   Matrix3x3 basis;
   Vector3 origin;
 };
@@ -642,9 +708,22 @@ template <class T> class Stamped : public T {
   ros::Time stamp_;
   std::string frame_id_;
 };
-inline geometry_msgs::Transform toMsg(const Transform&) { return geometry_msgs::Transform(); }
-inline geometry_msgs::TransformStamped toMsg(const Stamped<Transform>&) { return geometry_msgs::TransformStamped(); }
-inline void fromMsg(const geometry_msgs::TransformStamped&, Stamped<Transform>&) {}
+inline geometry_msgs::Transform toMsg(const Transform& t) {
+  geometry_msgs::Transform m;
+  m.translation.x = t.origin.x(); m.translation.y = t.origin.y(); m.translation.z = t.origin.z();
+  double q[4];
+  t.basis.getRotation(q);
+  m.rotation.x = q[0]; m.rotation.y = q[1]; m.rotation.z = q[2]; m.rotation.w = q[3];
+  return m;
+}
+inline geometry_msgs::TransformStamped toMsg(const Stamped<Transform>& t) {
+  geometry_msgs::TransformStamped m;
+  m.header.stamp = t.stamp_;
+  m.header.frame_id = t.frame_id_;
+  m.transform = toMsg(static_cast<const Transform&>(t));
+  return m;
+}
+inline void fromMsg(const geometry_msgs::TransformStamped&, Stamped<Transform>& out) { out.setIdentity(); }  // never reached: the stand-in tf buffer knows no frames
 
 // tf2_eigen: transformToEigen(geometry_msgs::Transform) =
 //   Isometry3d(Translation3d(t.x, t.y, t.z) * Quaterniond(q.w, q.x, q.y, q.z))
@@ -672,10 +751,31 @@ class Buffer {
   geometry_msgs::TransformStamped lookupTransform(const std::string&, const std::string&, const ros::Time&) const { return geometry_msgs::TransformStamped(); }
 };
 class TransformListener { public: explicit TransformListener(Buffer&) {} };
-class TransformBroadcaster { public: void sendTransform(const geometry_msgs::TransformStamped&) {} };
+class TransformBroadcaster {
+ public:
+  void sendTransform(const geometry_msgs::TransformStamped& m) { if (ros::PubLog* log = ros::mod_ref_pub_log()) log->add("/tf", m); }
+};
 }  // namespace tf2_ros
 
-// ------------------------------------------------------------------------------- upstream estimators (inert stubs)
+// ------------------------------------------------------------------------- upstream estimators (scripted stand-ins)
+// libviso2, sgm_gpu and pwc_net are inputs of this path.  Their stand-ins replay a script a test installs: frame k of
+// the script holds what each estimator returns on the k-th stereo frame (and whether it fails).  Every estimator
+// instance counts its own calls, so two nodes driven one after the other read the same script from the start.
+// Without a script they fail, as before.
+namespace mod_ref_upstream {
+struct Frame {
+  bool disparity_ok = false;
+  std::vector<float> disparity;            // width x height, dense
+  float f = 0, T = 0, min_disparity = 0, max_disparity = 0;
+  bool motion_ok = false;
+  double motion[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};  // libviso2 getMotion(): previous -> current
+  bool flow_ok = false;
+  std::vector<float> flow;                 // width x height x 2: optical flow of the previous frame -> this frame
+};
+struct Script { int width = 0, height = 0; std::vector<Frame> frames; };
+inline const Script*& script() { static const Script* s = nullptr; return s; }
+}  // namespace mod_ref_upstream
+
 struct Matrix { double val[4][4]; };  // libviso2 Matrix
 class Matcher {
  public:
@@ -690,21 +790,64 @@ class VisualOdometry {
 class VisualOdometryStereo : public VisualOdometry {
  public:
   struct parameters : public VisualOdometry::parameters { double base = 1; int ransac_iters = 0; double inlier_threshold = 0; bool reweighting = true; };
-  explicit VisualOdometryStereo(parameters) {}
-  bool process(uint8_t*, uint8_t*, int32_t*, bool = false) { return false; }
-  Matrix getMotion() { return Matrix(); }
+  explicit VisualOdometryStereo(parameters p) : param(p) {}
+  bool process(uint8_t* left, uint8_t* right, int32_t* dims, bool = false) {
+    const mod_ref_upstream::Script* s = mod_ref_upstream::script();
+    if (!s || calls_ >= s->frames.size()) return false;
+    last_ = &s->frames[calls_++];
+    // the images must be what the node was given: the script's frames are mono8 images whose first byte is the frame index
+    if (!left || !right || dims[0] != s->width || dims[1] != s->height || left[0] != (uint8_t)(calls_ - 1)) return false;
+    return last_->motion_ok;
+  }
+  Matrix getMotion() {
+    Matrix m;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m.val[i][j] = last_ ? last_->motion[i][j] : (i == j);
+    return m;
+  }
+  parameters param;
+ private:
+  size_t calls_ = 0;
+  const mod_ref_upstream::Frame* last_ = nullptr;
 };
 namespace sgm_gpu {
 class SgmGpu {
  public:
   explicit SgmGpu(const ros::NodeHandle&) {}
-  bool computeDisparity(const sensor_msgs::Image&, const sensor_msgs::Image&, const sensor_msgs::CameraInfo&, const sensor_msgs::CameraInfo&, stereo_msgs::DisparityImage&) { return false; }
+  // sgm_gpu stamps the DisparityImage (and its image) with the left image's header
+  bool computeDisparity(const sensor_msgs::Image& left, const sensor_msgs::Image&, const sensor_msgs::CameraInfo&, const sensor_msgs::CameraInfo&, stereo_msgs::DisparityImage& out) {
+    const mod_ref_upstream::Script* s = mod_ref_upstream::script();
+    if (!s || calls_ >= s->frames.size()) return false;
+    const mod_ref_upstream::Frame& fr = s->frames[calls_++];
+    if (!fr.disparity_ok) return false;
+    out.header = left.header;
+    out.image.header = left.header;
+    out.image.width = (uint32_t)s->width; out.image.height = (uint32_t)s->height;
+    out.image.encoding = "32FC1"; out.image.is_bigendian = 0; out.image.step = (uint32_t)s->width * 4;
+    out.image.data.resize((size_t)out.image.step * s->height);
+    std::memcpy(out.image.data.data(), fr.disparity.data(), out.image.data.size());
+    out.f = fr.f; out.T = fr.T; out.min_disparity = fr.min_disparity; out.max_disparity = fr.max_disparity; out.delta_d = 1.0f;
+    return true;
+  }
+ private:
+  size_t calls_ = 0;
 };
 }  // namespace sgm_gpu
 namespace pwc_net {
 class PwcNet {
  public:
-  bool estimateOpticalFlow(const sensor_msgs::Image&, const sensor_msgs::Image&, cv::Mat&) { return false; }
+  // first call = flow from frame 0 to frame 1 (the node has no previous image on frame 0)
+  bool estimateOpticalFlow(const sensor_msgs::Image&, const sensor_msgs::Image&, cv::Mat& flow) {
+    const mod_ref_upstream::Script* s = mod_ref_upstream::script();
+    if (!s || calls_ + 1 >= s->frames.size()) return false;
+    const mod_ref_upstream::Frame& fr = s->frames[++calls_];
+    if (!fr.flow_ok) return false;
+    flow.create(s->height, s->width, CV_32FC2);
+    for (int r = 0; r < s->height; r++)
+      std::memcpy(flow.data + (size_t)r * flow.step, fr.flow.data() + (size_t)r * s->width * 2, (size_t)s->width * 8);
+    return true;
+  }
+ private:
+  size_t calls_ = 0;
 };
 }  // namespace pwc_net
 

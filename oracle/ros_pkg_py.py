@@ -93,3 +93,20 @@ def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, nei
     return dict(status=rc, published=pub.value, header_ok=bool(hdr.value), objects=rec, objects_raw=raw.copy(),
                 n_objects=n.value, clusters_image=bgr, markers=[mpts[moff[i]:moff[i + 1]].copy() for i in range(m)],
                 marker_rgba=mrgba[:m].copy(), n_markers=nm.value)
+
+
+def node_sequence(disps, flows, motions, ok_flags, stamps, cam, f=1.0, T=1.0, min_disparity=0.0, max_disparity=128.0,
+                  subscribers=15, dynamic_flow_diff=-1):
+    """The PRODUCT's constructor node (ros/scene_flow_constructor) through stereoCallback; arguments and result as
+    ref_py.node_sequence."""
+    from ref_py import _node_sequence
+    return _node_sequence(load().rosb200_node_sequence, disps, flows, motions, ok_flags, stamps, cam, f, T,
+                          min_disparity, max_disparity, subscribers, dynamic_flow_diff)
+
+
+def constructor_defaults():
+    lib = load()
+    i2 = (C.c_int32 * 2)()
+    lib.rosb200_constructor_defaults.restype = C.c_int
+    assert lib.rosb200_constructor_defaults(i2) == 0
+    return dict(dynamic_flow_diff=i2[0], topics_ok=i2[1])

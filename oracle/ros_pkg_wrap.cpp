@@ -11,9 +11,11 @@
 #include <cstring>
 
 #include "clusterer_nodelet_b200.h"
+#include "scene_flow_constructor_b200_node.h"
 #include <visualization_msgs/MarkerArray.h>
 
 #include "msg_describe.h"
+#include "node_sequence.h"
 
 namespace {
 sensor_msgs::PointCloud2Ptr make_cloud_msg(int w, int h, const void* points32) {
@@ -218,6 +220,34 @@ int rosb200_cluster(int w, int h, const void* points32, int32_t cluster_size, do
   } catch (...) {
     return -11;
   }
+}
+
+/*
+ * The product's drop-in constructor NODE (moving_object_detector_b200/ros/scene_flow_constructor) driven through a
+ * sequence of stereo frames; same arguments and log format as ref_node_sequence (oracle/ref_full_wrap.cpp).
+ */
+int rosb200_node_sequence(int w, int h, int n_frames, const mod_node_sequence::camera* cam, float f, float T, float min_d,
+                          float max_d, const float* disparities, const float* flows, const double* motions,
+                          const int32_t* ok_flags, const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff,
+                          char* log, int log_cap, int32_t* shutdown_requested) {
+  auto finish = [](scene_flow_constructor::SceneFlowConstructor& node) {
+    if (node.construct_job_.valid()) node.construct_job_.wait();
+  };
+  return mod_node_sequence::run<scene_flow_constructor::SceneFlowConstructor>(
+      w, h, n_frames, cam, f, T, min_d, max_d, disparities, flows, motions, ok_flags, stamps, subscribers,
+      dynamic_flow_diff, finish, log, log_cap, shutdown_requested);
+}
+
+/* what the constructor node advertises and latches at start-up: out[0] = dynamic_flow_diff default, out[1] = number of
+ * the four topics advertised under the reference's names */
+int rosb200_constructor_defaults(int32_t* out2) {
+  scene_flow_constructor::SceneFlowConstructor n;
+  out2[0] = n.config_.dynamic_flow_diff;
+  out2[1] = (n.depth_pub_.state && n.depth_pub_.state->topic == "depth") +
+            (n.optflow_pub_.state && n.optflow_pub_.state->topic == "optical_flow") +
+            (n.pc_with_velocity_pub_.state && n.pc_with_velocity_pub_.state->topic == "scene_flow") +
+            (n.static_flow_pub_.state && n.static_flow_pub_.state->topic == "synthetic_optical_flow");
+  return 0;
 }
 
 }  // extern "C"
