@@ -145,6 +145,16 @@ float mod_host_sq_threshold(float thr);
 /* Pinned host memory for message buffers (lets H2D/D2H run at full PCIe rate); optional. */
 void* mod_host_alloc(size_t bytes);
 void mod_host_free(void* p);
+/* Pin / unpin a buffer the caller owns and keeps across frames (e.g. a message object that is reused): copies from /
+ * to it then are single DMAs.  Unregister before the memory is released.  MOD_OK or MOD_ERR_CUDA. */
+int mod_host_register(void* p, size_t bytes);
+int mod_host_unregister(void* p);
+/* Ordinary (pageable) buffers - the std::vector storage of ROS messages (scene_flow_constructor.cpp:351-362,
+ * clusterer_nodelet.cpp:225-226) - are staged through pinned memory by n host threads (the caller's included) while
+ * the copy engine moves the previous chunk; process-wide.  Default: $MOD_B200_COPY_THREADS, else min(4, hardware
+ * threads / 2).  n <= 0: plain cudaMemcpyAsync (the driver stages on one thread). */
+void mod_set_host_copy_threads(int n);
+int mod_host_copy_threads(void);
 
 /* ---- seam 1: SceneFlowConstructor::construct() minus ROS publishing (scene_flow_constructor.cpp:91-147) ------ */
 /* Host buffers in, host buffers out, synchronous.

@@ -96,6 +96,10 @@ PROTOTYPES = {
     "mod_host_sq_threshold": (C.c_float, [C.c_float]),
     "mod_host_alloc": (C.c_void_p, [C.c_size_t]),
     "mod_host_free": (None, [C.c_void_p]),
+    "mod_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mod_host_unregister": (C.c_int, [C.c_void_p]),
+    "mod_set_host_copy_threads": (None, [C.c_int]),
+    "mod_host_copy_threads": (C.c_int, []),
     "mod_scene_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(Disparity),
                                  C.POINTER(Disparity), C.c_void_p, C.c_int32, C.POINTER(Transform), C.c_double,
                                  C.POINTER(SfParams), C.c_void_p, C.c_void_p, C.c_void_p]),

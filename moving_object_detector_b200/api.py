@@ -176,6 +176,15 @@ class Context:
         """The context's own cudaStream_t as an integer handle."""
         return int(self._lib.mod_stream(self._h) or 0)
 
+    @staticmethod
+    def set_host_copy_threads(n: int) -> None:
+        """Host threads that stage pageable message buffers through pinned memory (process-wide; 0 = driver path)."""
+        _lib.load().mod_set_host_copy_threads(int(n))
+
+    @staticmethod
+    def host_copy_threads() -> int:
+        return _lib.load().mod_host_copy_threads()
+
     def set_static_flow_filter(self, enabled: bool) -> None:
         """Switches the filtered residual gate of the scene-flow kernel (outputs are identical either way)."""
         self._check(self._lib.mod_set_static_flow_filter(self._h, 1 if enabled else 0))
@@ -202,12 +211,15 @@ class Context:
     # ---- seam 1 ---------------------------------------------------------------------------------------------
     def scene_flow(self, now: DisparityImage, prev: DisparityImage, flow: np.ndarray, cam: CameraInfo,
                    prev2now: TransformMsg, dt_sec: float, config: SceneFlowConstructorConfig = None,
-                   want_depth: bool = False, want_static_flow: bool = False):
-        """SceneFlowConstructor::construct (scene_flow_constructor.cpp:91-147) -> (points32[H,W,8], depth, static)."""
+                   want_depth: bool = False, want_static_flow: bool = False, out: np.ndarray = None):
+        """SceneFlowConstructor::construct (scene_flow_constructor.cpp:91-147) -> (points32[H,W,8], depth, static).
+        `out`: a caller-owned (H,W,8) float32 array to fill instead of a fresh one (a message buffer kept across frames)."""
         config = config or SceneFlowConstructorConfig()
         h, w = now.image.shape
         assert flow.dtype == np.float32 and flow.shape == (h, w, 2) and flow.strides[1] == 8 and flow.strides[2] == 4
-        out = np.empty((h, w, 8), np.float32)
+        if out is None:
+            out = np.empty((h, w, 8), np.float32)
+        assert out.dtype == np.float32 and out.shape == (h, w, 8) and out.flags.c_contiguous
         depth = np.empty((h, w), np.float32) if want_depth else None
         static = np.empty((h, w, 2), np.float32) if want_static_flow else None
         cn, cp, cc, ct, cfg = now.to_c(), prev.to_c(), cam.to_c(), prev2now.to_c(), config.to_c()

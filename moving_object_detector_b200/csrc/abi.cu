@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostcopy.cuh"
 
 namespace mod {
 
@@ -88,6 +89,7 @@ struct mod_ctx {
   mod_object* d_objs = nullptr;
   mod_frame_stats* d_fstats = nullptr;
   mod_frame_stats* h_fstats = nullptr;  // pinned
+  HostStager stager;                    // pageable message buffers <-> device (hostcopy.cuh)
 
   // streaming buffers of mod_pipeline_sequence_host (lazily allocated)
   struct SeqBuf {
@@ -410,7 +412,11 @@ int upload_image(mod_ctx* ctx, cudaStream_t s, float* dst, const float* src, int
                  int channels) {
   const size_t row = static_cast<size_t>(w) * channels * sizeof(float);
   if (static_cast<size_t>(step_bytes) < row) return fail(ctx, MOD_ERR_INVALID_ARG, "row step %d smaller than a row", step_bytes);
-  MOD_CK(ctx, cudaMemcpy2DAsync(dst, row, src, static_cast<size_t>(step_bytes), row, h, cudaMemcpyHostToDevice, s));
+  if (static_cast<size_t>(step_bytes) == row) {  // dense rows (what cv_bridge and sgm_gpu emit): one staged copy
+    MOD_CK(ctx, ctx->stager.h2d(dst, src, row * h, s));
+  } else {
+    MOD_CK(ctx, cudaMemcpy2DAsync(dst, row, src, static_cast<size_t>(step_bytes), row, h, cudaMemcpyHostToDevice, s));
+  }
   return MOD_OK;
 }
 
@@ -474,6 +480,24 @@ void* mod_host_alloc(size_t bytes) {
 void mod_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
+int mod_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return MOD_ERR_INVALID_ARG;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return MOD_ERR_CUDA;
+  }
+  return MOD_OK;
+}
+int mod_host_unregister(void* p) {
+  if (!p) return MOD_ERR_INVALID_ARG;
+  if (cudaHostUnregister(p) != cudaSuccess) {
+    cudaGetLastError();
+    return MOD_ERR_CUDA;
+  }
+  return MOD_OK;
+}
+void mod_set_host_copy_threads(int n) { set_host_copy_threads(n); }
+int mod_host_copy_threads(void) { return host_copy_threads(); }
 
 const char* mod_last_error(const mod_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
@@ -632,9 +656,9 @@ int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_
   rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *params, 0.0, ctx->d_points, P, nullptr,
                           opt_depth ? ctx->d_depth : nullptr, opt_static_flow ? ctx->d_static : nullptr);
   if (rc != MOD_OK) return rc;
-  if (out_points32) MOD_CK(ctx, cudaMemcpyAsync(out_points32, ctx->d_points, P * 32, cudaMemcpyDeviceToHost, s));
-  if (opt_depth) MOD_CK(ctx, cudaMemcpyAsync(opt_depth, ctx->d_depth, P * 4, cudaMemcpyDeviceToHost, s));
-  if (opt_static_flow) MOD_CK(ctx, cudaMemcpyAsync(opt_static_flow, ctx->d_static, P * 8, cudaMemcpyDeviceToHost, s));
+  if (out_points32) MOD_CK(ctx, ctx->stager.d2h(out_points32, ctx->d_points, P * 32, s));
+  if (opt_depth) MOD_CK(ctx, ctx->stager.d2h(opt_depth, ctx->d_depth, P * 4, s));
+  if (opt_static_flow) MOD_CK(ctx, ctx->stager.d2h(opt_static_flow, ctx->d_static, P * 8, s));
   MOD_CK(ctx, cudaStreamSynchronize(s));
   return MOD_OK;
 }
@@ -648,12 +672,12 @@ int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_p
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
-  MOD_CK(ctx, cudaMemcpyAsync(ctx->d_points, points32, P * 32, cudaMemcpyHostToDevice, s));
+  MOD_CK(ctx, ctx->stager.h2d(ctx->d_points, points32, P * 32, s));
   const int32_t cap = max_objs < ctx->max_clusters ? max_objs : ctx->max_clusters;
   rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, nullptr, *params, opt_labels ? ctx->d_labels : nullptr,
                        ctx->d_objs, cap, ctx->d_fstats);
   if (rc != MOD_OK) return rc;
-  if (opt_labels) MOD_CK(ctx, cudaMemcpyAsync(opt_labels, ctx->d_labels, P * 4, cudaMemcpyDeviceToHost, s));
+  if (opt_labels) MOD_CK(ctx, ctx->stager.d2h(opt_labels, ctx->d_labels, P * 4, s));
   return fetch_objects(ctx, s, objs, cap, n_objs);
 }
 
@@ -682,8 +706,8 @@ int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_di
   rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, ctx->d_mask, *cl_params,
                        opt_labels ? ctx->d_labels : nullptr, ctx->d_objs, cap, ctx->d_fstats);
   if (rc != MOD_OK) return rc;
-  if (opt_out_points32) MOD_CK(ctx, cudaMemcpyAsync(opt_out_points32, ctx->d_points, P * 32, cudaMemcpyDeviceToHost, s));
-  if (opt_labels) MOD_CK(ctx, cudaMemcpyAsync(opt_labels, ctx->d_labels, P * 4, cudaMemcpyDeviceToHost, s));
+  if (opt_out_points32) MOD_CK(ctx, ctx->stager.d2h(opt_out_points32, ctx->d_points, P * 32, s));
+  if (opt_labels) MOD_CK(ctx, ctx->stager.d2h(opt_labels, ctx->d_labels, P * 4, s));
   return fetch_objects(ctx, s, objs, cap, n_objs);
 }
 
@@ -736,10 +760,10 @@ int mod_clusters_image(mod_ctx* ctx, int w, int h, const int32_t* labels, int32_
   const size_t P = static_cast<size_t>(w) * h;
   cudaStream_t s = ctx->stream;
   uint8_t* d_bgr = reinterpret_cast<uint8_t*>(ctx->d_points);  // 32 bytes per pixel of staging, 3 needed
-  MOD_CK(ctx, cudaMemcpyAsync(ctx->d_labels, labels, P * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  MOD_CK(ctx, ctx->stager.h2d(ctx->d_labels, labels, P * sizeof(int32_t), s));
   MOD_CK(ctx, launch_clusters_image(s, ctx->d_labels, nullptr, n_clusters, w, h, 1, d_bgr));
   ctx->launches++;
-  MOD_CK(ctx, cudaMemcpyAsync(out_bgr8, d_bgr, P * 3, cudaMemcpyDeviceToHost, s));
+  MOD_CK(ctx, ctx->stager.d2h(out_bgr8, d_bgr, P * 3, s));
   MOD_CK(ctx, cudaStreamSynchronize(s));
   return MOD_OK;
 }
@@ -787,13 +811,13 @@ int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data
   cudaStream_t s = ctx->stream;
   uint8_t* d_src = reinterpret_cast<uint8_t*>(ctx->d_points);
   uint8_t* d_out = d_src + 16 * static_cast<size_t>(ctx->max_w) * ctx->max_h;
-  MOD_CK(ctx, cudaMemcpyAsync(d_src, data, static_cast<size_t>(step_bytes) * h, cudaMemcpyHostToDevice, s));
+  MOD_CK(ctx, ctx->stager.h2d(d_src, data, static_cast<size_t>(step_bytes) * h, s));
   rc = mod_image_crop_batched_dev(ctx, s, w, h, 1, encoding, d_src, 0, step_bytes, target_w, target_h, d_out);
   if (rc != MOD_OK) return rc;
   const size_t out_bytes = static_cast<size_t>(target_w) * target_h * 3;
   if (out_bytes > 0) {
     if (!out_bgr8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
-    MOD_CK(ctx, cudaMemcpyAsync(out_bgr8, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    MOD_CK(ctx, ctx->stager.d2h(out_bgr8, d_out, out_bytes, s));
   }
   MOD_CK(ctx, cudaStreamSynchronize(s));
   return MOD_OK;

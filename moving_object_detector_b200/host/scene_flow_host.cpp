@@ -105,8 +105,8 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
     // depth output only depends on disparity_now (disparity_image_processor.cpp:105-121).
     if (!want_depth) return false;
     const uint32_t w = disparity_now->image.width, h = disparity_now->image.height;
-    std::vector<float> zero_flow(static_cast<size_t>(w) * h * 2, 0.0f);
-    sensor_msgs::Image depth;
+    zero_flow_.assign(static_cast<size_t>(w) * h * 2, 0.0f);
+    sensor_msgs::Image& depth = depth_msg_;
     std_msgs::Header hd;
     hd.frame_id = camera_frame_id_;
     hd.stamp = disparity_now->header.stamp;  // publishDepthImage(:431-438)
@@ -115,7 +115,7 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
     const mod_transform ident{0, 0, 0, 0, 0, 0, 1};
     const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
     const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &now,
-                                  zero_flow.data(), static_cast<int32_t>(w * 8), &ident, 1.0, &p, nullptr,
+                                  zero_flow_.data(), static_cast<int32_t>(w * 8), &ident, 1.0, &p, nullptr,
                                   reinterpret_cast<float*>(depth.data.data()), nullptr);
     if (rc != MOD_OK) {
       last_error_ = ctxError(ctx_, "mod_scene_flow(depth)", rc);
@@ -134,8 +134,12 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
   const bool want_cloud = pc_with_velocity_pub_.getNumSubscribers() > 0;    // :141
   const bool want_static = static_flow_pub_.getNumSubscribers() > 0;        // :144
 
-  sensor_msgs::PointCloud2 cloud;
-  sensor_msgs::Image depth, static_flow;
+  // The output messages live in the object and are refilled every frame: a fresh 32 B/px vector per frame costs more
+  // in page faults and zero-filling than the whole GPU path (profiles/r01_single_frame.jsonl).  publish(const M&)
+  // serialises before it returns, so the buffers are free again for the next frame.
+  sensor_msgs::PointCloud2& cloud = cloud_msg_;
+  sensor_msgs::Image& depth = depth_msg_;
+  sensor_msgs::Image& static_flow = static_flow_msg_;
   if (want_cloud) {
     describeVelocityCloud(cloud, w, h);
     cloud.header = left_flow->header;  // publishPointcloud(..., left_flow->header), :142

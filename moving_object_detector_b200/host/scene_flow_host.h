@@ -90,6 +90,10 @@ class SceneFlowConstructorB200 {
   mod_camera camera_{};
   std::string camera_frame_id_;
   std::string last_error_;
+  // output messages, kept across frames (construct() is never re-entered: one call at a time per object)
+  sensor_msgs::PointCloud2 cloud_msg_;
+  sensor_msgs::Image depth_msg_, static_flow_msg_;
+  std::vector<float> zero_flow_;
 };
 
 // pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZVelocity>) layout (pcl_point_xyz_velocity.h:8-34): fills everything

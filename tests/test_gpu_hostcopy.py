@@ -1,0 +1,73 @@
+"""Host seams with pageable message buffers staged by the library's own copy threads (csrc/hostcopy.cu): results must
+not depend on the thread count, the buffer kind (pageable / mod_host_alloc / mod_host_register) or the frame size
+(sizes that are not a multiple of the staging chunk, sizes below the staging threshold)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import seq_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_all(ctx, a, out=None):
+    cloud, depth, static = ctx.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"],
+                                          want_depth=True, want_static_flow=True, out=out)
+    cl = ctx.cluster(cloud, want_labels=True)
+    pl = ctx.pipeline(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"], want_points=True,
+                      want_labels=True)
+    return dict(cloud=cloud[..., [0, 1, 2, 4, 5, 6]].tobytes(), depth=depth.tobytes(), static=static.tobytes(),
+                labels=cl.labels.tobytes(), objs=cl.objects.tobytes(), p_cloud=pl.points32[..., [0, 1, 2, 4, 5, 6]].tobytes(),
+                p_labels=pl.labels.tobytes(), p_objs=pl.objects.tobytes())
+
+
+@pytest.mark.parametrize("size", [(640, 480), (1280, 720), (322, 203), (96, 64)])
+def test_results_do_not_depend_on_the_copy_threads(mod, size):
+    import dataclasses
+    from moving_object_detector_b200 import Context, synth
+    w, h = size
+    base = synth.CONFIGS["gazebo_640x480"]
+    cfg = dataclasses.replace(base, w=w, h=h, fx=base.fx * w / base.w, cx=base.cx * w / base.w, cy=base.cy * h / base.h)
+    a = seq_inputs(synth.make_sequence(cfg, 2), 0)
+    before = Context.host_copy_threads()
+    try:
+        with Context(w, h) as ctx:
+            Context.set_host_copy_threads(0)   # plain cudaMemcpyAsync: the driver stages
+            assert Context.host_copy_threads() == 0
+            want = _run_all(ctx, a)
+            for n in (1, 2, 4, 7):
+                Context.set_host_copy_threads(n)
+                assert Context.host_copy_threads() == n
+                got = _run_all(ctx, a)
+                for k in want:
+                    assert got[k] == want[k], (n, k)
+    finally:
+        Context.set_host_copy_threads(before)
+
+
+def test_pinned_and_registered_buffers_take_the_direct_path(mod):
+    from moving_object_detector_b200 import Context, DisparityImage, synth
+    lib = mod.load()
+    a = seq_inputs(synth.make_sequence(synth.CONFIGS["gazebo_640x480"], 2), 0)
+    h, w = a["now"].image.shape
+    with Context(w, h) as ctx:
+        want = _run_all(ctx, a)
+        # output buffer from mod_host_alloc, inputs registered in place
+        nbytes = w * h * 32
+        p = lib.mod_host_alloc(nbytes)
+        assert p
+        try:
+            out = np.frombuffer((C.c_uint8 * nbytes).from_address(p), np.float32).reshape(h, w, 8)
+            flow = np.ascontiguousarray(a["flow"])
+            assert lib.mod_host_register(flow.ctypes.data, flow.nbytes) == 0
+            try:
+                b = dict(a, flow=flow)
+                got = _run_all(ctx, b, out=out)
+            finally:
+                assert lib.mod_host_unregister(flow.ctypes.data) == 0
+            for k in want:
+                assert got[k] == want[k], k
+        finally:
+            lib.mod_host_free(p)
+    assert lib.mod_host_register(None, 16) != 0 and lib.mod_host_unregister(None) != 0
