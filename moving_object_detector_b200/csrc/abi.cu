@@ -899,14 +899,14 @@ int mod_pipeline_sequence_host(mod_ctx* ctx, int w, int h, int n_frames, const m
     // last slot.  The carry runs on the upload stream, i.e. after the previous chunk's upload and before the
     // next upload into that buffer, so no extra event is needed.
     if (c == 0) {
-      MOD_CK(ctx, cudaMemcpyAsync(b.d_disp, disp_frames, P * 4, cudaMemcpyHostToDevice, ctx->s_in));
+      MOD_CK(ctx, ctx->stager.h2d(b.d_disp, disp_frames, P * 4, ctx->s_in));
     } else {
       mod_ctx::SeqBuf& pb = ctx->seq[(c - 1) & 1];
       MOD_CK(ctx, cudaMemcpyAsync(b.d_disp, pb.d_disp + P * chunk, P * 4, cudaMemcpyDeviceToDevice, ctx->s_in));
     }
-    // frames first+1 .. first+n go to slots 1..n
-    MOD_CK(ctx, cudaMemcpyAsync(b.d_disp + P, disp_frames + P * (first + 1), P * 4 * n, cudaMemcpyHostToDevice, ctx->s_in));
-    MOD_CK(ctx, cudaMemcpyAsync(b.d_flow, flows + P * 2 * first, P * 8 * n, cudaMemcpyHostToDevice, ctx->s_in));
+    // frames first+1 .. first+n go to slots 1..n (pinned sources: one DMA each; pageable ones: staged, hostcopy.cuh)
+    MOD_CK(ctx, ctx->stager.h2d(b.d_disp + P, disp_frames + P * (first + 1), P * 4 * n, ctx->s_in));
+    MOD_CK(ctx, ctx->stager.h2d(b.d_flow, flows + P * 2 * first, P * 8 * n, ctx->s_in));
     MOD_CK(ctx, cudaEventRecord(b.ev_in, ctx->s_in));
 
     MOD_CK(ctx, cudaStreamWaitEvent(ctx->stream, b.ev_in, 0));
