@@ -493,8 +493,14 @@ __global__ void __launch_bounds__(kBlock)
 // only ever move towards the root), or unioned -- so the partition equals the one the reference's scan produces.
 // Pixels within N of the tile's top / left edge additionally run the implied-edge elimination of window_edges on their
 // cross-tile edges (they are listed separately so that interior warps do not pay for it).
+// Eight resident CTAs per SM (32 registers per thread, ~80 bytes of spill; 22 KB of shared memory at N = 4): the kernel
+// is a chain of short phases separated by barriers, and the barrier stall was its largest one at six CTAs per SM
+// (ncu, r01): 418 -> 390 us per 63 frames of 1280x720.
+#ifndef CL_TILE_MIN_BLOCKS
+#define CL_TILE_MIN_BLOCKS 8
+#endif
 template <int NC>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
     cl_tile_fast_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                         uint32_t* __restrict__ border_list, uint32_t* __restrict__ border_mask,
                         uint32_t* __restrict__ root_list, int* __restrict__ counters /* list, border, root */) {
@@ -514,8 +520,9 @@ __global__ void __launch_bounds__(kBlock)
   __shared__ uint8_t s_up[kIds];      // pixel has an accepted up-left neighbour
   __shared__ uint32_t s_E[kIds];      // accepted in-tile window cells minus the link
   __shared__ uint16_t s_dl[kPixels];  // interior pixels from the front, edge pixels from the back
-  __shared__ uint16_t s_bl[kPixels];
-  __shared__ uint32_t s_bx[kPixels];
+  constexpr int kEdgePixels = kPixels - (kTileW - NC) * (kTileH - NC);  // pixels within NC of the top / left tile edge
+  __shared__ uint16_t s_bl[kEdgePixels];
+  __shared__ uint32_t s_bx[kEdgePixels];
   __shared__ uint16_t s_rl[kPixels];
   __shared__ int s_ni, s_ne, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase;
   const int frame = blockIdx.z;
