@@ -1126,31 +1126,50 @@ __global__ void __launch_bounds__(kBlock)
   const int n = *list_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   const int lane = threadIdx.x & 31;
-  for (int t0 = blockIdx.x * kBlock; t0 < n; t0 += gridDim.x * kBlock) {
-    const int t = t0 + threadIdx.x;
-    int s = -1;
-    uint32_t frame = 0;
-    int i = 0;
-    if (t < n) {
-      const uint32_t g = list[t];
-      frame = g / P;
-      i = static_cast<int>(g - frame * P);
-      const uint32_t fbase = frame * P;
-      s = L.count[fbase + static_cast<uint32_t>(L.parent[fbase + static_cast<uint32_t>(L.parent[g])])];
+  // The look-up of one entry is a chain of four dependent loads (list -> tile root -> final root -> slot), so the
+  // kernel is bound by memory latency, not bandwidth: every thread keeps kScatterUnroll chains in flight.
+#ifndef CL_SCATTER_UNROLL
+#define CL_SCATTER_UNROLL 4
+#endif
+  constexpr int kU = CL_SCATTER_UNROLL;
+  for (int t0 = blockIdx.x * (kBlock * kU); t0 < n; t0 += gridDim.x * (kBlock * kU)) {
+    int s[kU], i[kU];
+    uint32_t frame[kU], g[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const int t = t0 + u * kBlock + threadIdx.x;
+      g[u] = t < n ? list[t] : 0xffffffffu;
     }
-    const unsigned member = __ballot_sync(kFull, s >= 0);
-    if (member == 0) continue;
-    const long long group = (s >= 0) ? ((static_cast<long long>(frame) << 32) | static_cast<unsigned>(s)) : (-1 - lane);
-    const unsigned same = __match_any_sync(kFull, group);
-    if (s >= 0) {
-      const int leader = __ffs(same) - 1;
-      const size_t cs = static_cast<size_t>(frame) * L.max_clusters + s;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(cursor + cs, __popc(same));
-      base = __shfl_sync(same, base, leader);
-      const size_t pos = static_cast<size_t>(frame) * P + member_offset[cs] + base + __popc(same & ((1u << lane) - 1));
-      member_speed[pos] = list_speed[t];  // |v| from cl_tile; speeds are >= 0: the bit pattern is monotone
-      member_pixel[pos] = i;
+    uint32_t r1[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      frame[u] = g[u] != 0xffffffffu ? g[u] / P : 0;
+      i[u] = static_cast<int>(g[u] - frame[u] * P);
+      r1[u] = g[u] != 0xffffffffu ? static_cast<uint32_t>(L.parent[g[u]]) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++)
+      if (g[u] != 0xffffffffu) r1[u] = static_cast<uint32_t>(L.parent[frame[u] * P + r1[u]]);
+#pragma unroll
+    for (int u = 0; u < kU; u++) s[u] = g[u] != 0xffffffffu ? L.count[frame[u] * P + r1[u]] : -1;
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const unsigned member = __ballot_sync(kFull, s[u] >= 0);
+      if (member == 0) continue;
+      const long long group =
+          (s[u] >= 0) ? ((static_cast<long long>(frame[u]) << 32) | static_cast<unsigned>(s[u])) : (-1 - lane);
+      const unsigned same = __match_any_sync(kFull, group);
+      if (s[u] >= 0) {
+        const int leader = __ffs(same) - 1;
+        const size_t cs = static_cast<size_t>(frame[u]) * L.max_clusters + s[u];
+        int base = 0;
+        if (lane == leader) base = atomicAdd(cursor + cs, __popc(same));
+        base = __shfl_sync(same, base, leader);
+        const size_t pos =
+            static_cast<size_t>(frame[u]) * P + member_offset[cs] + base + __popc(same & ((1u << lane) - 1));
+        member_speed[pos] = list_speed[t0 + u * kBlock + threadIdx.x];  // |v| from cl_tile; >= 0: bit pattern monotone
+        member_pixel[pos] = i[u];
+      }
     }
   }
 }
