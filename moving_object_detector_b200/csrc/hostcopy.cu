@@ -219,9 +219,9 @@ cudaError_t HostStager::ensure(int threads) {
 
 cudaError_t HostStager::h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return cudaSuccess;
-  const int T = host_copy_threads();
-  if (T <= 0 || bytes < kMinBytes || is_pinned(h_src))
-    return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
+  // (the pool is only started when a pageable buffer actually shows up)
+  const int T = (bytes < kMinBytes || is_pinned(h_src)) ? 0 : host_copy_threads();
+  if (T <= 0) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
   cudaError_t e = ensure(T);
   if (e != cudaSuccess) return e;
   const size_t wave = static_cast<size_t>(T) * kChunk;
@@ -245,8 +245,8 @@ cudaError_t HostStager::h2d(void* d_dst, const void* h_src, size_t bytes, cudaSt
 
 cudaError_t HostStager::d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t stream) {
   if (bytes == 0) return cudaSuccess;
-  const int T = host_copy_threads();
-  if (T <= 0 || bytes < kMinBytes || is_pinned(h_dst)) {
+  const int T = (bytes < kMinBytes || is_pinned(h_dst)) ? 0 : host_copy_threads();
+  if (T <= 0) {
     const cudaError_t e = cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
     return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
   }
