@@ -71,3 +71,39 @@ def test_pinned_and_registered_buffers_take_the_direct_path(mod):
         finally:
             lib.mod_host_free(p)
     assert lib.mod_host_register(None, 16) != 0 and lib.mod_host_unregister(None) != 0
+
+
+def test_sequence_host_call_gives_the_same_objects_from_pageable_and_pinned_frames(mod):
+    """mod_pipeline_sequence_host stages pageable frames itself and sends pinned ones with one DMA each: same results,
+    with the copy threads on and off."""
+    import dataclasses
+    import torch
+    from moving_object_detector_b200 import (CameraInfo, ClustererConfig, Context, OBJECT_DTYPE, STATS_DTYPE,
+                                             SceneFlowConstructorConfig, TransformMsg, synth)
+    cfg = dataclasses.replace(synth.CONFIGS["gazebo_640x480"], seed=2103)
+    n_pairs, max_objs = 5, 64
+    seq = synth.make_sequence(cfg, n_pairs + 1)
+    disp, flows = seq["disp"].contiguous(), seq["flows"].contiguous()
+    H, W = disp.shape[1:]
+    before = Context.host_copy_threads()
+
+    def run(d, f):
+        objs = np.zeros((n_pairs, max_objs), OBJECT_DTYPE)
+        stats = np.zeros(n_pairs, STATS_DTYPE)
+        with Context(W, H, max_batch=2) as c:
+            c.pipeline_sequence_host(d, f, CameraInfo.pinhole(*seq["cam"]),
+                                     [TransformMsg(t[:3], t[3:]) for t in seq["transforms"]], seq["dts"], seq["f"],
+                                     seq["T"], seq["min_disparity"], seq["max_disparity"], SceneFlowConstructorConfig(),
+                                     ClustererConfig(), objs, stats, max_objs)
+        return objs.tobytes(), stats.tobytes()
+
+    try:
+        Context.set_host_copy_threads(0)
+        want = run(disp.numpy(), flows.numpy())
+        assert np.frombuffer(want[1], STATS_DTYPE)["n_objects"].sum() > 0
+        for threads in (1, 4):
+            Context.set_host_copy_threads(threads)
+            assert run(disp.numpy(), flows.numpy()) == want, threads
+        assert run(disp.pin_memory(), flows.pin_memory()) == want
+    finally:
+        Context.set_host_copy_threads(before)
