@@ -36,6 +36,7 @@
 //   cl_objects   one CTA per cluster: 3-pass (11/11/10 bit) radix select of the (n/2)-th largest |v|, MovingObject
 //   cl_labels    optional dense label image (cluster_map_)
 
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -1186,6 +1187,34 @@ constexpr int kObjBlock = 1024;
 constexpr int kSmemMembers = 9216;  // 36 KB
 constexpr int kBins = 2048;
 
+// Which of the two cl_objects kernels runs is decided on the device, identically by every CTA of both (the other one
+// returns at once): cooperating CTAs pay ~8 cluster barriers per object, which only a long member list amortises, and
+// a cluster of kObjCluster CTAs leaves 2 * 148 / kObjCluster objects in flight.  Measured (profiles/r01_clusterer.md):
+// 3840x2160 frames (objects of ~250 k members) 0.34 -> 0.21 ms per frame, 63 frames of 1280x720 (230 objects of ~30 k)
+// 0.57 -> 0.73 ms if forced.
+constexpr int kObjCluster = 8;
+constexpr int kObjClusterMinMembers = 96 * 1024;      // the largest object must be at least this long ...
+constexpr int kObjClusterMaxObjects = 2 * (2 * 148 / kObjCluster);  // ... and the objects fit in two rounds
+// Frames below this size (1280x720 and smaller: an object of 96 k members would be a tenth of the frame) never launch
+// the cluster variant, so the common configurations pay nothing for the choice.
+constexpr size_t kObjClusterMinPixels = 3u << 19;  // 1.5 Mpx
+__device__ __forceinline__ bool objects_use_clusters(const ClLaunch& L, int n_work, const int2* __restrict__ work_items) {
+  __shared__ int s_max_members;
+  if (threadIdx.x == 0) s_max_members = 0;
+  __syncthreads();
+  if (n_work <= kObjClusterMaxObjects) {
+    int mx = 0;
+    for (int i = threadIdx.x; i < n_work; i += blockDim.x) {
+      const int2 w = work_items[i];
+      mx = max(mx, L.stats[static_cast<size_t>(w.x) * L.max_clusters + w.y].count);
+    }
+    if (mx > 0) atomicMax(&s_max_members, mx);
+  }
+  __syncthreads();
+  return s_max_members >= kObjClusterMinMembers;
+}
+
+template <bool kClustersPossible>  // false: the instantiation small frames run never looks at the choice
 __global__ void __launch_bounds__(kObjBlock, 2)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
                       int* __restrict__ work_cursor, const int* __restrict__ member_offset,
@@ -1199,6 +1228,9 @@ __global__ void __launch_bounds__(kObjBlock, 2)
   __shared__ int s_best;
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const int n_work = *work_count;
+  if constexpr (kClustersPossible) {
+    if (objects_use_clusters(L, n_work, work_items)) return;  // cl_objects_cluster_kernel takes this batch
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(work_cursor, 1);
@@ -1321,6 +1353,174 @@ __global__ void __launch_bounds__(kObjBlock, 2)
   }
 }
 
+// ---- cl_objects on thread-block clusters ----------------------------------------------------------------------------
+// Same computation, one cluster of kC CTAs per moving-object cluster: the member list is cut into kC contiguous slices,
+// every CTA histograms its slice into its own shared memory, and rank 0 reads the other CTAs' histograms through
+// distributed shared memory for the suffix scan; the selection state (prefix, k, tie-break minimum) lives in rank 0's
+// shared memory and is read / updated by the others through DSMEM, with the hardware cluster barrier between the
+// phases.  A frame's few largest objects no longer serialise on one CTA each (the kernel's time was the longest list).
+namespace cg = cooperative_groups;
+
+template <int kC>
+__global__ void __launch_bounds__(kObjBlock, 2)
+    cl_objects_cluster_kernel(const ClLaunch L, const int* __restrict__ work_count,
+                              const int2* __restrict__ work_items, int* __restrict__ work_cursor,
+                              const int* __restrict__ member_offset, const uint32_t* __restrict__ member_speed,
+                              const int* __restrict__ member_pixel) {
+  __shared__ uint32_t s_speed[kSmemMembers];
+  __shared__ unsigned hist[kBins];
+  __shared__ unsigned s_wsum[kObjBlock / 32];
+  __shared__ int s_item;
+  __shared__ uint32_t s_prefix;
+  __shared__ uint32_t s_k;
+  __shared__ int s_best;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank();
+  const int* item0 = cluster.map_shared_rank(&s_item, 0);
+  const uint32_t* prefix0 = cluster.map_shared_rank(&s_prefix, 0);
+  int* best0 = cluster.map_shared_rank(&s_best, 0);
+  const size_t P = static_cast<size_t>(L.w) * L.h;
+  const int n_work = *work_count;
+  if (!objects_use_clusters(L, n_work, work_items)) return;  // cl_objects_kernel takes this batch (no DSMEM touched yet)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (;;) {
+    if (crank == 0 && threadIdx.x == 0) {
+      const int it = atomicAdd(work_cursor, 1);
+      s_item = it;
+      s_prefix = 0;
+      s_best = 0x7fffffff;
+      if (it < n_work) {
+        const int2 w0 = work_items[it];
+        s_k = static_cast<uint32_t>(L.stats[static_cast<size_t>(w0.x) * L.max_clusters + w0.y].count / 2);
+      }
+    }
+    cluster.sync();
+    const int item = *item0;
+    if (item >= n_work) {  // the same for every CTA of the cluster
+      cluster.sync();      // rank 0's shared memory must outlive the other CTAs' read of it
+      return;
+    }
+    const int2 w = work_items[item];
+    const int frame = w.x, slot = w.y;
+    ClusterStat& st = L.stats[static_cast<size_t>(frame) * L.max_clusters + slot];
+    const int n = st.count;
+    const size_t off = frame * P + member_offset[static_cast<size_t>(frame) * L.max_clusters + slot];
+    // this CTA's slice of the member list
+    const int len = (n + kC - 1) / kC;
+    const int begin = min(n, static_cast<int>(crank) * len), end = min(n, begin + len);
+    const int m = end - begin;
+    const uint32_t* gspeeds = member_speed + off + begin;
+    const int* pixels = member_pixel + off + begin;
+    const bool staged = m <= kSmemMembers;
+    if (staged)
+      for (int j = threadIdx.x; j < m; j += kObjBlock) s_speed[j] = gspeeds[j];
+    const uint32_t* speeds = staged ? s_speed : gspeeds;
+    int decided = 0;  // number of high bits already fixed
+    for (int pass = 0; pass < 3; pass++) {
+      const int bits = pass < 2 ? 11 : 10;
+      const int shift = 32 - decided - bits;
+      for (int b = threadIdx.x; b < kBins; b += kObjBlock) hist[b] = 0;
+      __syncthreads();
+      const uint32_t prefix = *prefix0;
+      const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
+      const uint32_t binmask = (1u << bits) - 1u;
+      for (int j0 = 0; j0 < m; j0 += 4 * kObjBlock) {
+        uint32_t v[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int j = j0 + q * kObjBlock + threadIdx.x;
+          ok[q] = j < m;
+          v[q] = ok[q] ? speeds[j] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          int bin = -1;
+          if (ok[q] && (v[q] & himask) == prefix) bin = static_cast<int>((v[q] >> shift) & binmask);
+          int uniform;
+          __match_all_sync(kFull, bin, &uniform);
+          if (uniform) {
+            if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
+          } else if (bin >= 0) {
+            atomicAdd(&hist[bin], 1u);
+          }
+        }
+      }
+      cluster.sync();  // every CTA's histogram is complete
+      if (crank == 0) {
+        // parallel suffix scan over the summed histograms: thread t owns bins hi = kBins-1-2t and hi-1
+        const int hi = kBins - 1 - 2 * static_cast<int>(threadIdx.x);
+        unsigned h0 = hist[hi], h1 = hist[hi - 1];
+#pragma unroll
+        for (int r = 1; r < kC; r++) {
+          const unsigned* rh = cluster.map_shared_rank(hist, r);
+          h0 += rh[hi];
+          h1 += rh[hi - 1];
+        }
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+          unsigned ws = s_wsum[lane];
+          unsigned wi = ws;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFull, wi, o);
+            if (lane >= o) wi += t;
+          }
+          s_wsum[lane] = wi - ws;  // exclusive
+        }
+        __syncthreads();
+        const unsigned before = s_wsum[warp] + incl - (h0 + h1);  // members in bins above `hi`
+        const uint32_t k = s_k;
+        __syncthreads();  // every thread has read s_k before it is overwritten
+        if (k >= before && k < before + h0) {
+          s_k = k - before;
+          s_prefix = prefix | (static_cast<uint32_t>(hi) << shift);
+        } else if (k >= before + h0 && k < before + h0 + h1) {
+          s_k = k - before - h0;
+          s_prefix = prefix | (static_cast<uint32_t>(hi - 1) << shift);
+        }
+      }
+      decided += bits;
+      cluster.sync();  // the new prefix is visible; rank 0 has finished reading the other histograms
+    }
+    const uint32_t target = *prefix0;
+    int best = 0x7fffffff;
+    for (int j = threadIdx.x; j < m; j += kObjBlock)
+      if (speeds[j] == target) best = min(best, pixels[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
+    if (lane == 0 && best != 0x7fffffff) atomicMin(best0, best);
+    cluster.sync();
+    if (crank == 0 && threadIdx.x == 0) {
+      const int id = st.rank;
+      st.median_idx = s_best;
+      if (id >= 0 && id < L.max_objs) {
+        mod_object o;
+        o.id = id;
+        const float* rec = L.points + (static_cast<size_t>(frame) * L.points_frame_stride + s_best) * 8;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const float mn = ordered_to_float(st.mn[k]);
+          const float mx = ordered_to_float(st.mx[k]);
+          o.bbox[k] = __fsub_rn(mx, mn);
+          o.center[k] = __fdiv_rn(__fadd_rn(mn, mx), 2.0f);
+          o.velocity[k] = rec[4 + k];
+        }
+        o.n_points = n;
+        L.objs[static_cast<size_t>(frame) * L.max_objs + id] = o;
+      }
+    }
+    // the other CTAs touch rank 0's control words again only after the cluster barrier at the top of the loop
+  }
+}
+
 // ---- cl_labels --------------------------------------------------------------------------------------------------
 // Final cluster_map_ (after removeSmallClusters' relabel, :386-392), dense, -1 = NOT_BELONGED_.
 __global__ void __launch_bounds__(kBlock) cl_labels_kernel(const ClLaunch L) {
@@ -1435,14 +1635,38 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
                                                                                           X.member_offset);
   cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, X.list_speed, counters, X.member_offset, X.cursor, X.member_speed,
                                                  X.member_pixel);
-  cl_objects_kernel<<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
-                                              X.member_speed, X.member_pixel);
+  const bool clusters_possible = static_cast<size_t>(L.w) * L.h >= kObjClusterMinPixels;
+  if (!clusters_possible) {
+    cl_objects_kernel<false><<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
+                                                       X.member_speed, X.member_pixel);
+  } else {  // plus the thread-block-cluster variant; exactly one of the two processes the batch
+    cl_objects_kernel<true><<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
+                                                      X.member_speed, X.member_pixel);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 148 / kObjCluster * kObjCluster);
+    cfg.blockDim = dim3(kObjBlock);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kObjCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, cl_objects_cluster_kernel<kObjCluster>, L,
+                                             static_cast<const int*>(X.work_count), static_cast<const int2*>(X.work_items),
+                                             X.work_cursor, static_cast<const int*>(X.member_offset),
+                                             static_cast<const uint32_t*>(X.member_speed),
+                                             static_cast<const int*>(X.member_pixel));
+    if (e != cudaSuccess) return e;
+  }
   if (L.labels != nullptr) {
     size_t lb = (total + kBlock - 1) / kBlock;
     if (lb > 148 * 16) lb = 148 * 16;
     cl_labels_kernel<<<static_cast<unsigned>(lb), kBlock, 0, s>>>(L);
   }
-  if (n_launches) *n_launches = 8 + (L.labels != nullptr ? 1 : 0);
+  if (n_launches) *n_launches = 8 + (clusters_possible ? 1 : 0) + (L.labels != nullptr ? 1 : 0);
   return cudaGetLastError();
 }
 

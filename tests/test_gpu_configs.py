@@ -324,3 +324,37 @@ def test_every_neighbor_distance_path_matches_oracle(oracle, n, size):
     assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
     if n > 0:
         assert want["n_objects"] > 3
+
+
+@pytest.mark.parametrize("sizes", [(131072,), (150000, 98304, 3000), (300000, 2600, 2600, 2600, 120000)])
+def test_long_member_lists_take_the_cluster_kernel_and_match_the_oracle(oracle, sizes):
+    """Objects of >= 96 k members on a frame of >= 1.5 Mpx are reduced by cooperating CTAs of a thread-block cluster
+    (cl_objects_cluster_kernel: sliced member list, histograms summed through distributed shared memory).  Blobs with
+    random speeds (a meaningful median), ties at the median, slices that do not divide evenly, short lists beside
+    long ones."""
+    W, H = 2048, 1024
+    rng = np.random.RandomState(len(sizes) * 7 + 1)
+    cloud = np.zeros((H, W, 8), np.float32)
+    cloud[..., 2] = 5.0
+    cloud[..., 0] = (np.arange(W, dtype=np.float32) - W / 2)[None, :] * 0.01
+    cloud[..., 1] = (np.arange(H, dtype=np.float32) - H / 2)[:, None] * 0.01
+    y0 = 8
+    for k, n in enumerate(sizes):
+        bw = 1900 if n > 20000 else 60
+        bh = -(-n // bw)
+        assert y0 + bh + 8 < H
+        ys, xs = np.divmod(np.arange(n), bw)
+        speed = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        if k == 0:
+            speed[: n // 3] = np.float32(1.25)   # a third of the members tie at one speed
+        ang = rng.uniform(0, 2 * np.pi, n)
+        cloud[y0 + ys, 16 + xs, 4] = speed * np.cos(ang).astype(np.float32)
+        cloud[y0 + ys, 16 + xs, 5] = speed * np.sin(ang).astype(np.float32)
+        cloud[y0 + ys, 16 + xs, 2] = 5.0 + 0.001 * k
+        y0 += bh + 12   # > neighbor_distance rows apart: separate clusters
+    want = oracle.cluster(cloud)
+    assert want["n_objects"] == len(sizes) and sorted(int(o["n_points"]) for o in want["objects"]) == sorted(sizes)
+    with Context(W, H) as c:
+        got = c.cluster(cloud, want_labels=True)
+    assert np.array_equal(got.labels, want["labels"])
+    assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
