@@ -155,6 +155,13 @@ int mod_host_unregister(void* p);
  * threads / 2).  n <= 0: plain cudaMemcpyAsync (the driver stages on one thread). */
 void mod_set_host_copy_threads(int n);
 int mod_host_copy_threads(void);
+/* Frame identities for the NEXT mod_scene_flow / mod_pipeline call on this context (then forgotten): caller-chosen
+ * non-zero ids of the two disparity images' contents, e.g. the messages' stamps in nanoseconds.  The image uploaded
+ * as `now` stays on the device; when the following call names the same id as `prev_id` (same size) it is not uploaded
+ * again - the reference keeps `disparity_previous_ = disparity_now_` the same way (scene_flow_constructor.cpp:398).
+ * The ids are a promise about contents: equal ids, equal images.  Without ids (or with 0) both images are uploaded. */
+int mod_set_frame_ids(mod_ctx* ctx, unsigned long long now_id, unsigned long long prev_id);
+unsigned long long mod_resident_hits(const mod_ctx* ctx); /* uploads saved so far (diagnostic) */
 
 /* ---- seam 1: SceneFlowConstructor::construct() minus ROS publishing (scene_flow_constructor.cpp:91-147) ------ */
 /* Host buffers in, host buffers out, synchronous.

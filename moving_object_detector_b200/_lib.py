@@ -100,6 +100,8 @@ PROTOTYPES = {
     "mod_host_unregister": (C.c_int, [C.c_void_p]),
     "mod_set_host_copy_threads": (None, [C.c_int]),
     "mod_host_copy_threads": (C.c_int, []),
+    "mod_set_frame_ids": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_ulonglong]),
+    "mod_resident_hits": (C.c_ulonglong, [C.c_void_p]),
     "mod_scene_flow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(Disparity),
                                  C.POINTER(Disparity), C.c_void_p, C.c_int32, C.POINTER(Transform), C.c_double,
                                  C.POINTER(SfParams), C.c_void_p, C.c_void_p, C.c_void_p]),

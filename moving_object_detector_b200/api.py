@@ -185,6 +185,15 @@ class Context:
     def host_copy_threads() -> int:
         return _lib.load().mod_host_copy_threads()
 
+    def set_frame_ids(self, now_id: int, prev_id: int) -> None:
+        """Identities of the next scene_flow / pipeline call's disparity images (e.g. stamps in ns): a `prev` that was the
+        previous call's `now` is then reused on the device instead of uploaded again."""
+        self._check(self._lib.mod_set_frame_ids(self._h, int(now_id), int(prev_id)))
+
+    @property
+    def resident_hits(self) -> int:
+        return int(self._lib.mod_resident_hits(self._h))
+
     def set_static_flow_filter(self, enabled: bool) -> None:
         """Switches the filtered residual gate of the scene-flow kernel (outputs are identical either way)."""
         self._check(self._lib.mod_set_static_flow_filter(self._h, 1 if enabled else 0))

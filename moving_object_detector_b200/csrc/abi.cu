@@ -90,6 +90,13 @@ struct mod_ctx {
   mod_frame_stats* d_fstats = nullptr;
   mod_frame_stats* h_fstats = nullptr;  // pinned
   HostStager stager;                    // pageable message buffers <-> device (hostcopy.cuh)
+  // Frame identities for the host seams (mod_set_frame_ids): the disparity image uploaded as `now` stays on the device
+  // and is reused when the next call names it as `prev` - in a stream every frame is uploaded once, as in the batched
+  // sequence path, instead of twice.
+  unsigned long long next_now_id = 0, next_prev_id = 0;  // consumed by the next mod_scene_flow / mod_pipeline call
+  unsigned long long resident_id = 0;   // id of the image held in d_disp slot `resident_slot` (0: none)
+  int resident_slot = 0, resident_w = 0, resident_h = 0;
+  unsigned long long resident_hits = 0;
 
   // streaming buffers of mod_pipeline_sequence_host (lazily allocated)
   struct SeqBuf {
@@ -420,6 +427,34 @@ int upload_image(mod_ctx* ctx, cudaStream_t s, float* dst, const float* src, int
   return MOD_OK;
 }
 
+// Uploads the two disparity images of a host-seam call into the context's two staging slots and says which slot holds
+// which.  With frame identities (mod_set_frame_ids) a `prev` that is the previous call's `now` is already there.
+int upload_disparities(mod_ctx* ctx, cudaStream_t s, int w, int h, const mod_disparity& now, const mod_disparity& prev,
+                       const float** d_now, const float** d_prev) {
+  const unsigned long long now_id = ctx->next_now_id, prev_id = ctx->next_prev_id;
+  ctx->next_now_id = ctx->next_prev_id = 0;
+  float* slots[2] = {ctx->d_disp_now, ctx->d_disp_prev};
+  int sp = 0;
+  const bool reuse = prev_id != 0 && prev_id == ctx->resident_id && w == ctx->resident_w && h == ctx->resident_h;
+  ctx->resident_id = 0;  // nothing is promised while the slots are being rewritten (or if an upload fails)
+  int rc;
+  if (reuse) {
+    sp = ctx->resident_slot;
+    ctx->resident_hits++;
+  } else if ((rc = upload_image(ctx, s, slots[sp], prev.data, prev.step_bytes, w, h, 1)) != MOD_OK) {
+    return rc;
+  }
+  const int sn = sp ^ 1;
+  if ((rc = upload_image(ctx, s, slots[sn], now.data, now.step_bytes, w, h, 1)) != MOD_OK) return rc;
+  ctx->resident_id = now_id;
+  ctx->resident_slot = sn;
+  ctx->resident_w = w;
+  ctx->resident_h = h;
+  *d_now = slots[sn];
+  *d_prev = slots[sp];
+  return MOD_OK;
+}
+
 mod_pair_dev make_pair(const float* d_now, const float* d_prev, const float* d_flow, const mod_disparity& now,
                        const mod_disparity& prev, const mod_transform& T, double dt) {
   mod_pair_dev p;
@@ -496,6 +531,13 @@ int mod_host_unregister(void* p) {
   }
   return MOD_OK;
 }
+int mod_set_frame_ids(mod_ctx* ctx, unsigned long long now_id, unsigned long long prev_id) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  ctx->next_now_id = now_id;
+  ctx->next_prev_id = prev_id;
+  return MOD_OK;
+}
+unsigned long long mod_resident_hits(const mod_ctx* ctx) { return ctx ? ctx->resident_hits : 0; }
 void mod_set_host_copy_threads(int n) { set_host_copy_threads(n); }
 int mod_host_copy_threads(void) { return host_copy_threads(); }
 
@@ -649,10 +691,10 @@ int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
-  if ((rc = upload_image(ctx, s, ctx->d_disp_now, now->data, now->step_bytes, w, h, 1)) != MOD_OK) return rc;
-  if ((rc = upload_image(ctx, s, ctx->d_disp_prev, prev->data, prev->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  const float *d_now = nullptr, *d_prev = nullptr;
+  if ((rc = upload_disparities(ctx, s, w, h, *now, *prev, &d_now, &d_prev)) != MOD_OK) return rc;
   if ((rc = upload_image(ctx, s, ctx->d_flow, flow_xy, flow_step_bytes, w, h, 2)) != MOD_OK) return rc;
-  const mod_pair_dev pair = make_pair(ctx->d_disp_now, ctx->d_disp_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
+  const mod_pair_dev pair = make_pair(d_now, d_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
   rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *params, 0.0, ctx->d_points, P, nullptr,
                           opt_depth ? ctx->d_depth : nullptr, opt_static_flow ? ctx->d_static : nullptr);
   if (rc != MOD_OK) return rc;
@@ -695,10 +737,10 @@ int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_di
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
-  if ((rc = upload_image(ctx, s, ctx->d_disp_now, now->data, now->step_bytes, w, h, 1)) != MOD_OK) return rc;
-  if ((rc = upload_image(ctx, s, ctx->d_disp_prev, prev->data, prev->step_bytes, w, h, 1)) != MOD_OK) return rc;
+  const float *d_now = nullptr, *d_prev = nullptr;
+  if ((rc = upload_disparities(ctx, s, w, h, *now, *prev, &d_now, &d_prev)) != MOD_OK) return rc;
   if ((rc = upload_image(ctx, s, ctx->d_flow, flow_xy, flow_step_bytes, w, h, 2)) != MOD_OK) return rc;
-  const mod_pair_dev pair = make_pair(ctx->d_disp_now, ctx->d_disp_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
+  const mod_pair_dev pair = make_pair(d_now, d_prev, ctx->d_flow, *now, *prev, *prev2now, dt_sec);
   rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *sf_params, cl_params->dynamic_speed, ctx->d_points, P,
                           ctx->d_mask, nullptr, nullptr);
   if (rc != MOD_OK) return rc;

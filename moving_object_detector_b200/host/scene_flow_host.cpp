@@ -20,6 +20,11 @@ mod_ctx* createContext(int max_w, int max_h, int device) {
   return ctx;
 }
 
+// identity of a disparity message for mod_set_frame_ids: its stamp in nanoseconds (0 = unknown, never reused)
+unsigned long long frameId(const stereo_msgs::DisparityImage& d) {
+  return static_cast<unsigned long long>(d.header.stamp.sec) * 1000000000ull + d.header.stamp.nsec;
+}
+
 mod_disparity toC(const stereo_msgs::DisparityImage& d) {
   mod_disparity c;
   c.f = d.f;
@@ -114,6 +119,7 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
     const mod_disparity now = toC(*disparity_now);
     const mod_transform ident{0, 0, 0, 0, 0, 0, 1};
     const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
+    mod_set_frame_ids(ctx_, frameId(*disparity_now), frameId(*disparity_now));
     const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &now,
                                   zero_flow_.data(), static_cast<int32_t>(w * 8), &ident, 1.0, &p, nullptr,
                                   reinterpret_cast<float*>(depth.data.data()), nullptr);
@@ -160,6 +166,8 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
   // (stamp_now - stamp_previous).toSec(), :162-164
   const double dt = (disparity_now->header.stamp - disparity_previous->header.stamp).toSec();
   const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
+  // in a stream the previous disparity is the one the last call uploaded as `now`: it is still on the device
+  mod_set_frame_ids(ctx_, frameId(*disparity_now), frameId(*disparity_previous));
   const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &prev,
                                 reinterpret_cast<const float*>(left_flow->data.data()),
                                 static_cast<int32_t>(left_flow->step), &tr, dt, &p,

@@ -50,9 +50,24 @@ for name in ("gazebo_640x480", "zed_1280x720", "zed2k_2208x1242"):
             cl = timed(lambda: ctx.cluster(cloud, want_labels=False), 20)
             pl = timed(lambda: ctx.pipeline(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"],
                                             want_labels=False), 20)
+            # a stream: frame ids (mod_set_frame_ids) let the previous disparity stay on the device; the two images
+            # alternate as now / prev so that every call keeps the promise "equal ids, equal contents"
+            state = {"k": 1}
+
+            def stream_call(fn):
+                k = state["k"]
+                state["k"] = k + 1
+                ctx.set_frame_ids(k + 1, k)
+                now, prev = (a["now"], a["prev"]) if k % 2 else (a["prev"], a["now"])
+                return fn(now, prev)
+            pl_stream = timed(lambda: stream_call(lambda now, prev: ctx.pipeline(
+                now, prev, a["flow"], a["cam"], a["prev2now"], a["dt_sec"], want_labels=False)), 20)
+            sf_stream = timed(lambda: stream_call(lambda now, prev: ctx.scene_flow(
+                now, prev, a["flow"], a["cam"], a["prev2now"], a["dt_sec"], out=kept)), 20)
             line["copy_threads_%d%s" % (threads, " (driver staging)" if threads == 0 else "")] = {
                 "mod_scene_flow_ms": sf[0], "mod_scene_flow_fresh_output_ms": sf_fresh[0], "mod_cluster_ms": cl[0],
-                "two_node_ms": sf[0] + cl[0], "mod_pipeline_ms": pl[0]}
+                "two_node_ms": sf[0] + cl[0], "mod_pipeline_ms": pl[0],
+                "stream_mod_scene_flow_ms": sf_stream[0], "stream_mod_pipeline_ms": pl_stream[0]}
         Context.set_host_copy_threads(default_threads)
         line["default_copy_threads"] = default_threads
         n_obj = ctx.pipeline(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"], want_labels=False).n_objects

@@ -107,3 +107,48 @@ def test_sequence_host_call_gives_the_same_objects_from_pageable_and_pinned_fram
         assert run(disp.pin_memory(), flows.pin_memory()) == want
     finally:
         Context.set_host_copy_threads(before)
+
+
+def test_previous_disparity_stays_resident_with_frame_ids(mod):
+    """mod_set_frame_ids: in a stream the image uploaded as `now` is reused as the next call's `prev`.  Same results as
+    without ids; the reuse happens (resident_hits); a wrong promise is not made by the library itself: without ids,
+    or after a size change, everything is uploaded."""
+    import dataclasses
+    from moving_object_detector_b200 import Context, DisparityImage, synth
+    cfg = dataclasses.replace(synth.CONFIGS["gazebo_640x480"], seed=2104)
+    n = 5
+    seq = synth.make_sequence(cfg, n + 1)
+    H, W = seq["disp"].shape[1:]
+
+    def run(use_ids, fused):
+        outs = []
+        with Context(W, H) as c:
+            for i in range(n):
+                a = seq_inputs(seq, i)
+                if use_ids:
+                    c.set_frame_ids(1000 + i + 1, 1000 + i)
+                if fused:
+                    r = c.pipeline(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"], want_points=True)
+                    outs.append((r.points32[..., [0, 1, 2, 4, 5, 6]].tobytes(), r.labels.tobytes(), r.objects.tobytes()))
+                else:
+                    cloud = c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])[0]
+                    outs.append(cloud[..., [0, 1, 2, 4, 5, 6]].tobytes())
+            return outs, c.resident_hits
+
+    for fused in (False, True):
+        want, hits0 = run(False, fused)
+        got, hits = run(True, fused)
+        assert hits0 == 0 and hits == n - 1
+        assert got == want
+
+    # ids that do not chain (prev_id is not the previous now_id), and a call without ids in between: no reuse
+    with Context(W, H) as c:
+        for i in range(3):
+            a = seq_inputs(seq, i)
+            c.set_frame_ids(50 + 2 * i, 7)
+            c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])
+        a = seq_inputs(seq, 3)
+        c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])   # no ids: forgets
+        c.set_frame_ids(60, 54)
+        c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])
+        assert c.resident_hits == 0
