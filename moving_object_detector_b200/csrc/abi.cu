@@ -97,6 +97,11 @@ struct mod_ctx {
   unsigned long long resident_id = 0;   // id of the image held in d_disp slot `resident_slot` (0: none)
   int resident_slot = 0, resident_w = 0, resident_h = 0;
   unsigned long long resident_hits = 0;
+  // the clusterer's kernel sequence of the last small-batch call as an instantiated CUDA graph (run_cluster_dev)
+  cudaGraphExec_t cl_graph = nullptr;
+  ClLaunch cl_graph_L;
+  ClExtra cl_graph_X;
+  int cl_graph_launches = 0;
 
   // streaming buffers of mod_pipeline_sequence_host (lazily allocated)
   struct SeqBuf {
@@ -335,6 +340,11 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
   return MOD_OK;
 }
 
+#ifndef MOD_CLUSTER_GRAPH_MAX_BATCH
+#define MOD_CLUSTER_GRAPH_MAX_BATCH 8
+#endif
+constexpr int kClusterGraphMaxBatch = MOD_CLUSTER_GRAPH_MAX_BATCH;  // 0: never replay a graph
+
 int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const float* d_points,
                     size_t frame_stride_points, const uint8_t* d_mask, const mod_cl_params& params,
                     int32_t* d_labels, mod_object* d_objs, int32_t max_objs, mod_frame_stats* d_stats) {
@@ -392,8 +402,38 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
   X.member_pixel = ctx->d_member_pixel;
   (void)P;
   int n_launches = 0;
-  MOD_CK(ctx, launch_cluster(s, L, X, &n_launches));
-  ctx->launches += n_launches;
+  // Small batches (a live node: one frame per call) are bound by launch latency - eight to ten kernels of a few
+  // microseconds each.  Their launch parameters are a pure function of (L, X), which only change with the frame size,
+  // the reconfigure values or the caller's buffers, so the sequence is captured once into a CUDA graph and replayed.
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  const bool graph_ok = batch <= kClusterGraphMaxBatch && s != nullptr &&
+                        cudaStreamIsCapturing(s, &capturing) == cudaSuccess && capturing == cudaStreamCaptureStatusNone;
+  if (!graph_ok) {
+    MOD_CK(ctx, launch_cluster(s, L, X, &n_launches));
+    ctx->launches += n_launches;
+    return MOD_OK;
+  }
+  if (!ctx->cl_graph || std::memcmp(&ctx->cl_graph_L, &L, sizeof(L)) != 0 ||
+      std::memcmp(&ctx->cl_graph_X, &X, sizeof(X)) != 0) {
+    if (ctx->cl_graph) {
+      cudaGraphExecDestroy(ctx->cl_graph);
+      ctx->cl_graph = nullptr;
+    }
+    MOD_CK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const cudaError_t launched = launch_cluster(s, L, X, &n_launches);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ended = cudaStreamEndCapture(s, &graph);
+    MOD_CK(ctx, launched);
+    MOD_CK(ctx, ended);
+    const cudaError_t inst = cudaGraphInstantiate(&ctx->cl_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    MOD_CK(ctx, inst);
+    ctx->cl_graph_L = L;
+    ctx->cl_graph_X = X;
+    ctx->cl_graph_launches = n_launches;
+  }
+  MOD_CK(ctx, cudaGraphLaunch(ctx->cl_graph, s));
+  ctx->launches += ctx->cl_graph_launches;
   return MOD_OK;
 }
 
@@ -673,6 +713,7 @@ void mod_destroy(mod_ctx* ctx) {
     if (b.ev_comp) cudaEventDestroy(b.ev_comp);
     if (b.ev_out) cudaEventDestroy(b.ev_out);
   }
+  if (ctx->cl_graph) cudaGraphExecDestroy(ctx->cl_graph);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
