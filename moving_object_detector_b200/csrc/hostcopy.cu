@@ -152,7 +152,9 @@ class CopyPool {
       Job* job = nullptr;
       {
         std::unique_lock<std::mutex> l(mu_);
-        if (!woke) cv_job_.wait(l, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+        // stop_ is part of the condition: a worker that starts after the epoch of a resize was published would
+        // otherwise record that epoch as seen and sleep through its own stop request
+        if (!woke) cv_job_.wait(l, [&] { return stop_ || epoch_.load(std::memory_order_acquire) != seen; });
         seen = epoch_.load(std::memory_order_acquire);
         if (stop_) return;
         job = job_;  // registering under mu_ keeps the job alive until active drops back (see run)

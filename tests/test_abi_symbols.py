@@ -121,3 +121,18 @@ def test_sqrt_free_threshold(mod):
         for s in cand + [np.float32(0.0), np.float32(np.inf)]:
             assert (np.sqrt(s) >= thr) == (s >= s2), (thr, s, s2)
     assert np.isnan(lib.mod_host_sq_threshold(np.float32(np.nan)))
+
+
+def test_host_copy_thread_setting_needs_no_gpu(mod):
+    """mod_set_host_copy_threads / mod_host_copy_threads are host-only (csrc/hostcopy.cu): the pool can be sized,
+    clamped to [0, 16] and switched off without a device; frame ids and hits are per-context and need one."""
+    lib = mod.load()
+    before = lib.mod_host_copy_threads()
+    try:
+        for n, want in ((3, 3), (1, 1), (0, 0), (-5, 0), (100, 16), (4, 4)):
+            lib.mod_set_host_copy_threads(n)
+            assert lib.mod_host_copy_threads() == want
+    finally:
+        lib.mod_set_host_copy_threads(before)
+    assert lib.mod_set_frame_ids(None, 1, 2) != 0 and lib.mod_resident_hits(None) == 0
+    assert lib.mod_host_register(None, 0) != 0
