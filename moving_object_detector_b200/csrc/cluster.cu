@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
   __shared__ uint16_t s_bl[kEdgePixels];
   __shared__ uint32_t s_bx[kEdgePixels];
   __shared__ uint16_t s_rl[kPixels];
-  __shared__ int s_ni, s_ne, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase;
+  __shared__ int s_ni, s_ne, s_bcnt, s_rcnt, s_base, s_bbase, s_rbase, s_first;
   const int frame = blockIdx.z;
   const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
   const size_t P = static_cast<size_t>(L.w) * L.h;
@@ -792,11 +792,25 @@ __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
   __syncthreads();
   for (int e = threadIdx.x; e < nd; e += kBlock) {  // F
     const int c = pixel_at(e);
-    s_lab[c] = smem_find_readonly(s_lab, c);
+    const int r = smem_find_readonly(s_lab, c);
+    s_lab[c] = r;
+    if (e == 0) s_first = r;
   }
   __syncthreads();
+#ifndef CL_TILE_NO_UNIFORM_SKIP
+  // One component in the tile (the usual case inside a blob): every accepted in-tile edge joins equal labels, so
+  // the compare round has nothing to find.
+  bool one_label = true;
+  {
+    const int first = s_first;
+    for (int e = threadIdx.x; e < nd; e += kBlock) one_label = one_label && (s_lab[pixel_at(e)] == first);
+  }
+  const bool skip_compare = __syncthreads_and(one_label);
+#else
+  const bool skip_compare = false;
+#endif
   bool unioned = false;
-  for (int e0 = 0; e0 < nd; e0 += kBlock) {  // C2b: whatever still differs
+  for (int e0 = 0; e0 < (skip_compare ? 0 : nd); e0 += kBlock) {  // C2b: whatever still differs
     const int e = e0 + threadIdx.x;
     int c = 0;
     uint32_t diff = 0;
