@@ -43,7 +43,10 @@ class HostStager {
   uint8_t* window_ = nullptr;     // 2 halves of threads_ * kChunk bytes, pinned
   cudaEvent_t done_[2] = {nullptr, nullptr};  // last DMA that used each half
   int threads_ = 0;
-  static constexpr size_t kChunk = 512u << 10;  // bytes one thread copies per wave
+#ifndef MOD_COPY_CHUNK_KB
+#define MOD_COPY_CHUNK_KB 512
+#endif
+  static constexpr size_t kChunk = static_cast<size_t>(MOD_COPY_CHUNK_KB) << 10;  // bytes one thread copies per wave
 };
 
 }  // namespace mod
