@@ -19,6 +19,12 @@
 namespace mod {
 namespace {
 
+inline void cpu_relax() {
+#ifdef MOD_HAVE_SSE2_STREAM
+  _mm_pause();  // spin-wait hint: leaves the core's resources to the sibling hyper-thread
+#endif
+}
+
 // memcpy whose stores bypass the cache (SSE2 non-temporal, baseline x86-64): the destination - the pinned window on
 // the way in, the message buffer on the way out - is not read again by this thread, so it should neither be fetched
 // for ownership nor displace the source lines.  One third less memory traffic than a cached copy.
@@ -90,12 +96,12 @@ class CopyPool {
     }
     cv_job_.notify_all();
     work(job);
-    while (job.pending.load(std::memory_order_acquire) > 0) {}  // stragglers are inside a memcpy of <= 512 KB
+    while (job.pending.load(std::memory_order_acquire) > 0) cpu_relax();  // stragglers are inside one chunk's memcpy
     {
       std::lock_guard<std::mutex> l(mu_);  // from here on no worker can pick the job up ...
       job_ = nullptr;
     }
-    while (job.active.load(std::memory_order_acquire) > 0) {}  // ... and those that did have left it
+    while (job.active.load(std::memory_order_acquire) > 0) cpu_relax();  // ... and those that did have left it
   }
 
  private:
@@ -148,6 +154,7 @@ class CopyPool {
       bool woke = false;
       while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(200)) {
         if (epoch_.load(std::memory_order_acquire) != seen) { woke = true; break; }
+        cpu_relax();
       }
       Job* job = nullptr;
       {
