@@ -182,6 +182,12 @@ int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_
  *  objs/n_objs: MovingObjectArray.moving_object_array in id order. */
 int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_params* params, int32_t* opt_labels,
                 mod_object* objs, int32_t max_objs, int32_t* n_objs);
+/* The same on the cloud the last mod_scene_flow call on this context left on the device (whether or not it was
+ * downloaded): constructor and clusterer in one process, the reference's two nodes without the PointCloud2 round
+ * trip between them (scene_flow_constructor.cpp:141-142 -> clusterer_nodelet.cpp:221-242).  MOD_ERR_INVALID_ARG when
+ * there is no such cloud of this size. */
+int mod_cluster_resident(mod_ctx* ctx, int w, int h, const mod_cl_params* params, int32_t* opt_labels,
+                         mod_object* objs, int32_t max_objs, int32_t* n_objs);
 
 /* ---- fused host entry: seam 1 + seam 2 with the cloud staying on the GPU ------------------------------------ */
 /* opt_out_points32 is only copied back when non-NULL (the reference publishes ~scene_flow only when it has

@@ -107,6 +107,8 @@ PROTOTYPES = {
                                  C.POINTER(SfParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mod_cluster": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(ClParams), C.c_void_p,
                               C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "mod_cluster_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ClParams), C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.POINTER(C.c_int32)]),
     "mod_pipeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(Disparity),
                                C.POINTER(Disparity), C.c_void_p, C.c_int32, C.POINTER(Transform), C.c_double,
                                C.POINTER(SfParams), C.POINTER(ClParams), C.c_void_p, C.c_void_p, C.c_void_p,

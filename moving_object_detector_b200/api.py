@@ -258,6 +258,22 @@ class Context:
         res.n_objects = n.value
         return res
 
+    def cluster_resident(self, w: int, h: int, config: ClustererConfig = None, want_labels: bool = True,
+                         max_objs: int = 1024) -> ClusterResult:
+        """The clusterer on the cloud the last scene_flow() call left on the device (no PointCloud2 round trip)."""
+        config = config or ClustererConfig()
+        labels = np.empty((h, w), np.int32) if want_labels else None
+        objs = np.zeros(max_objs, OBJECT_DTYPE)
+        n = C.c_int32(0)
+        cfg = config.to_c()
+        rc = self._check(self._lib.mod_cluster_resident(self._h, w, h, C.byref(cfg),
+                                                        labels.ctypes.data if want_labels else None, objs.ctypes.data,
+                                                        max_objs, C.byref(n)), allow=(_lib.MOD_ERR_CAPACITY,))
+        res = ClusterResult(objs[:min(n.value, max_objs)], labels)
+        res.status = rc
+        res.n_objects = n.value
+        return res
+
     def clusters_image(self, labels: np.ndarray, n_clusters: int) -> np.ndarray:
         """ClustererNodelet::publishClustersImage (clusterer_nodelet.cpp:293-322): (H,W) int32 labels -> (H,W,3) BGR8."""
         labels = np.ascontiguousarray(labels, np.int32)

@@ -97,6 +97,7 @@ struct mod_ctx {
   unsigned long long resident_id = 0;   // id of the image held in d_disp slot `resident_slot` (0: none)
   int resident_slot = 0, resident_w = 0, resident_h = 0;
   unsigned long long resident_hits = 0;
+  int cloud_w = 0, cloud_h = 0;         // size of the cloud the last mod_scene_flow left in d_points (0: none)
   // the clusterer's kernel sequence of the last small-batch call as an instantiated CUDA graph (run_cluster_dev)
   cudaGraphExec_t cl_graph = nullptr;
   ClLaunch cl_graph_L;
@@ -739,11 +740,31 @@ int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_
   rc = run_scene_flow_dev(ctx, s, w, h, 1, *cam, &pair, *params, 0.0, ctx->d_points, P, nullptr,
                           opt_depth ? ctx->d_depth : nullptr, opt_static_flow ? ctx->d_static : nullptr);
   if (rc != MOD_OK) return rc;
+  ctx->cloud_w = w;
+  ctx->cloud_h = h;
   if (out_points32) MOD_CK(ctx, ctx->stager.d2h(out_points32, ctx->d_points, P * 32, s));
   if (opt_depth) MOD_CK(ctx, ctx->stager.d2h(opt_depth, ctx->d_depth, P * 4, s));
   if (opt_static_flow) MOD_CK(ctx, ctx->stager.d2h(opt_static_flow, ctx->d_static, P * 8, s));
   MOD_CK(ctx, cudaStreamSynchronize(s));
   return MOD_OK;
+}
+
+int mod_cluster_resident(mod_ctx* ctx, int w, int h, const mod_cl_params* params, int32_t* opt_labels,
+                         mod_object* objs, int32_t max_objs, int32_t* n_objs) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!params || max_objs < 0 || (max_objs > 0 && !objs)) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  if (ctx->cloud_w != w || ctx->cloud_h != h)
+    return fail(ctx, MOD_ERR_INVALID_ARG, "no %dx%d cloud from a previous mod_scene_flow call on this context", w, h);
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t P = static_cast<size_t>(w) * h;
+  const int32_t cap = max_objs < ctx->max_clusters ? max_objs : ctx->max_clusters;
+  rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, nullptr, *params, opt_labels ? ctx->d_labels : nullptr,
+                       ctx->d_objs, cap, ctx->d_fstats);
+  if (rc != MOD_OK) return rc;
+  if (opt_labels) MOD_CK(ctx, ctx->stager.d2h(opt_labels, ctx->d_labels, P * 4, s));
+  return fetch_objects(ctx, s, objs, cap, n_objs);
 }
 
 int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_params* params, int32_t* opt_labels,
@@ -755,6 +776,7 @@ int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_p
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
+  ctx->cloud_w = ctx->cloud_h = 0;  // replaced by the caller's cloud
   MOD_CK(ctx, ctx->stager.h2d(ctx->d_points, points32, P * 32, s));
   const int32_t cap = max_objs < ctx->max_clusters ? max_objs : ctx->max_clusters;
   rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, nullptr, *params, opt_labels ? ctx->d_labels : nullptr,
@@ -789,6 +811,8 @@ int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_di
   rc = run_cluster_dev(ctx, s, w, h, 1, ctx->d_points, P, ctx->d_mask, *cl_params,
                        opt_labels ? ctx->d_labels : nullptr, ctx->d_objs, cap, ctx->d_fstats);
   if (rc != MOD_OK) return rc;
+  ctx->cloud_w = w;
+  ctx->cloud_h = h;
   if (opt_out_points32) MOD_CK(ctx, ctx->stager.d2h(opt_out_points32, ctx->d_points, P * 32, s));
   if (opt_labels) MOD_CK(ctx, ctx->stager.d2h(opt_labels, ctx->d_labels, P * 4, s));
   return fetch_objects(ctx, s, objs, cap, n_objs);
@@ -842,6 +866,7 @@ int mod_clusters_image(mod_ctx* ctx, int w, int h, const int32_t* labels, int32_
   if (rc != MOD_OK) return rc;
   const size_t P = static_cast<size_t>(w) * h;
   cudaStream_t s = ctx->stream;
+  ctx->cloud_w = ctx->cloud_h = 0;  // the cloud buffer doubles as staging here
   uint8_t* d_bgr = reinterpret_cast<uint8_t*>(ctx->d_points);  // 32 bytes per pixel of staging, 3 needed
   MOD_CK(ctx, ctx->stager.h2d(ctx->d_labels, labels, P * sizeof(int32_t), s));
   MOD_CK(ctx, launch_clusters_image(s, ctx->d_labels, nullptr, n_clusters, w, h, 1, d_bgr));
@@ -892,6 +917,7 @@ int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data
   // staging: the 32 bytes-per-pixel cloud buffer holds the source (at most 16 bytes per pixel of row stride) in its
   // first half and the crop (3 bytes per pixel) in its second half
   cudaStream_t s = ctx->stream;
+  ctx->cloud_w = ctx->cloud_h = 0;  // the cloud buffer doubles as staging here
   uint8_t* d_src = reinterpret_cast<uint8_t*>(ctx->d_points);
   uint8_t* d_out = d_src + 16 * static_cast<size_t>(ctx->max_w) * ctx->max_h;
   MOD_CK(ctx, ctx->stager.h2d(d_src, data, static_cast<size_t>(step_bytes) * h, s));

@@ -25,6 +25,32 @@ unsigned long long frameId(const stereo_msgs::DisparityImage& d) {
   return static_cast<unsigned long long>(d.header.stamp.sec) * 1000000000ull + d.header.stamp.nsec;
 }
 
+// mod_object records -> MovingObjectArray: float -> float64 widening as in the reference's assignments
+// (clusterer_nodelet.cpp:151-181), identity orientation, header = the cloud's (:327)
+void fillMovingObjects(const mod_object* objs, int32_t n, const std_msgs::Header& header,
+                       moving_object_msgs::MovingObjectArray& out) {
+  out.header = header;
+  out.moving_object_array.resize(static_cast<size_t>(n));
+  for (int32_t i = 0; i < n; i++) {
+    const mod_object& o = objs[i];
+    moving_object_msgs::MovingObject& m = out.moving_object_array[static_cast<size_t>(i)];
+    m.id = o.id;
+    m.center.position.x = o.center[0];
+    m.center.position.y = o.center[1];
+    m.center.position.z = o.center[2];
+    m.center.orientation.x = 0;
+    m.center.orientation.y = 0;
+    m.center.orientation.z = 0;
+    m.center.orientation.w = 1;
+    m.velocity.x = o.velocity[0];
+    m.velocity.y = o.velocity[1];
+    m.velocity.z = o.velocity[2];
+    m.bounding_box.x = o.bbox[0];
+    m.bounding_box.y = o.bbox[1];
+    m.bounding_box.z = o.bbox[2];
+  }
+}
+
 mod_disparity toC(const stereo_msgs::DisparityImage& d) {
   mod_disparity c;
   c.f = d.f;
@@ -181,6 +207,21 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
   if (want_depth) depth_pub_.publish(depth);
   if (want_cloud) pc_with_velocity_pub_.publish(cloud);
   if (want_static) static_flow_pub_.publish(static_flow);
+  if (moving_objects_pub_.getNumSubscribers() > 0) {  // the clusterer, in process, on the cloud still on the GPU
+    const mod_cl_params cp{clusterer_cluster_size, clusterer_depth_diff, clusterer_dynamic_speed,
+                           clusterer_neighbor_distance};
+    std::vector<mod_object> objs(4096);
+    int32_t n = 0;
+    const int rc2 = mod_cluster_resident(ctx_, static_cast<int>(w), static_cast<int>(h), &cp, nullptr, objs.data(),
+                                         static_cast<int32_t>(objs.size()), &n);
+    if (rc2 != MOD_OK) {
+      last_error_ = ctxError(ctx_, "mod_cluster_resident", rc2);
+      return true;  // the scene flow itself was computed and published
+    }
+    moving_object_msgs::MovingObjectArray out;
+    fillMovingObjects(objs.data(), n, left_flow->header, out);  // the header ~scene_flow carries
+    moving_objects_pub_.publish(out);
+  }
   return true;
 }
 
@@ -328,26 +369,7 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
   }
   if (!want_objects) return true;
   moving_object_msgs::MovingObjectArray out;
-  out.header = msg.header;  // moving_objects_msg.header = input_header_, :327
-  out.moving_object_array.resize(static_cast<size_t>(n));
-  for (int32_t i = 0; i < n; i++) {
-    const mod_object& o = objs[static_cast<size_t>(i)];
-    moving_object_msgs::MovingObject& m = out.moving_object_array[static_cast<size_t>(i)];
-    m.id = o.id;
-    m.center.position.x = o.center[0];  // float -> float64, as the reference's assignments do (:151-181)
-    m.center.position.y = o.center[1];
-    m.center.position.z = o.center[2];
-    m.center.orientation.x = 0;
-    m.center.orientation.y = 0;
-    m.center.orientation.z = 0;
-    m.center.orientation.w = 1;
-    m.velocity.x = o.velocity[0];
-    m.velocity.y = o.velocity[1];
-    m.velocity.z = o.velocity[2];
-    m.bounding_box.x = o.bbox[0];
-    m.bounding_box.y = o.bbox[1];
-    m.bounding_box.z = o.bbox[2];
-  }
+  fillMovingObjects(objs.data(), n, msg.header, out);  // moving_objects_msg.header = input_header_, :327
   dynamic_objects_pub_.publish(out);
   return true;
 }

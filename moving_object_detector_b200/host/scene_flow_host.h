@@ -78,6 +78,14 @@ class SceneFlowConstructorB200 {
   Sink<sensor_msgs::Image> depth_pub_;            // ~depth                   32FC1
   Sink<sensor_msgs::PointCloud2> pc_with_velocity_pub_;  // ~scene_flow       PointXYZVelocity, point_step 32
   Sink<sensor_msgs::Image> static_flow_pub_;      // ~synthetic_optical_flow  32FC2
+  // Optional: the clusterer in the same process (mod_cluster_resident on the cloud construct() just left on the GPU),
+  // so that ~scene_flow's 32 B/px never cross the PCIe link or a ROS socket unless somebody subscribes to it.  When
+  // this sink is set and subscribed, construct() publishes what ClustererNodelet::dataCB would have published on
+  // ~moving_objects for that cloud, after its own topics.  clusterer_* are the Clusterer.cfg parameters.
+  Sink<moving_object_msgs::MovingObjectArray> moving_objects_pub_;
+  int clusterer_cluster_size = 2500;
+  double clusterer_depth_diff = 0.15, clusterer_dynamic_speed = 0.3;
+  int clusterer_neighbor_distance = 4;
 
   const std::string& lastError() const { return last_error_; }
   mod_ctx* context() const { return ctx_; }

@@ -68,6 +68,14 @@ class SceneFlowConstructor {
 
   // outputs
   ros::Publisher optflow_pub_, depth_pub_, pc_with_velocity_pub_, static_flow_pub_;
+  // ~fused_clusterer (default false): also run the clusterer in this process, on the cloud still on the GPU, and
+  // publish ~moving_objects (remap it to where scene_flow_clusterer's ~moving_objects went); its four parameters are
+  // served by a second dynamic_reconfigure server under ~clusterer.  The separate clusterer node is then not needed
+  // and ~scene_flow's 32 B/px only leave the GPU while somebody subscribes to it.
+  bool fused_clusterer_ = false;
+  ros::Publisher moving_objects_pub_;
+  std::shared_ptr<dynamic_reconfigure::Server<scene_flow_clusterer::ClustererConfig>> clusterer_reconfigure_server_;
+  scene_flow_clusterer::ClustererConfig clusterer_config_;  // guarded by config_mutex_
 
   // inputs: stereo images + camera infos, exact-time synchronised
   std::shared_ptr<image_transport::ImageTransport> image_transport_;

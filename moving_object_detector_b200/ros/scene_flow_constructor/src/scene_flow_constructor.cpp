@@ -62,6 +62,16 @@ SceneFlowConstructor::SceneFlowConstructor() {
   optflow_pub_ = pnh.advertise<sensor_msgs::Image>("optical_flow", 1);
   pc_with_velocity_pub_ = pnh.advertise<sensor_msgs::PointCloud2>("scene_flow", 1);
   static_flow_pub_ = pnh.advertise<sensor_msgs::Image>("synthetic_optical_flow", 1);
+  pnh.param("fused_clusterer", fused_clusterer_, false);
+  if (fused_clusterer_) {
+    moving_objects_pub_ = pnh.advertise<moving_object_msgs::MovingObjectArray>("moving_objects", 1);
+    clusterer_reconfigure_server_ =
+        std::make_shared<dynamic_reconfigure::Server<scene_flow_clusterer::ClustererConfig>>(ros::NodeHandle(pnh, "clusterer"));
+    clusterer_reconfigure_server_->setCallback([this](scene_flow_clusterer::ClustererConfig& config, uint32_t) {
+      std::lock_guard<std::mutex> lock(config_mutex_);
+      clusterer_config_ = config;
+    });
+  }
 
   const std::string left_topic = nh.resolveName("left_image"), right_topic = nh.resolveName("right_image");
   left_image_sub_.subscribe(*image_transport_, left_topic, 1);
@@ -144,6 +154,10 @@ void SceneFlowConstructor::construct(DisparityPtr disparity_now, DisparityPtr di
   {
     std::lock_guard<std::mutex> lock(config_mutex_);
     engine_->reconfigureCB(config_, 0);
+    engine_->clusterer_cluster_size = clusterer_config_.cluster_size;
+    engine_->clusterer_depth_diff = clusterer_config_.depth_diff;
+    engine_->clusterer_dynamic_speed = clusterer_config_.dynamic_speed;
+    engine_->clusterer_neighbor_distance = clusterer_config_.neighbor_distance;
   }
   // every output is produced only while somebody listens (reference :99, :114, :141, :144)
   engine_->optflow_pub_ = {[this](const sensor_msgs::Image& m) { optflow_pub_.publish(m); },
@@ -154,6 +168,9 @@ void SceneFlowConstructor::construct(DisparityPtr disparity_now, DisparityPtr di
                                     static_cast<int>(pc_with_velocity_pub_.getNumSubscribers())};
   engine_->static_flow_pub_ = {[this](const sensor_msgs::Image& m) { static_flow_pub_.publish(m); },
                                static_cast<int>(static_flow_pub_.getNumSubscribers())};
+  if (fused_clusterer_)
+    engine_->moving_objects_pub_ = {[this](const moving_object_msgs::MovingObjectArray& m) { moving_objects_pub_.publish(m); },
+                                    static_cast<int>(moving_objects_pub_.getNumSubscribers())};
   engine_->construct(disparity_now, disparity_previous, left_flow, transform_prev2now);
   if (!engine_->lastError().empty()) ROS_ERROR("scene_flow_constructor: %s", engine_->lastError().c_str());
 }

@@ -6,6 +6,7 @@
 // TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <geometry_msgs/TransformStamped.h>
+#include <moving_object_msgs/MovingObjectArray.h>
 #include <sensor_msgs/CameraInfo.h>
 #include <sensor_msgs/Image.h>
 #include <sensor_msgs/PointCloud2.h>
@@ -70,6 +71,22 @@ inline std::string render(const std::string& topic, const std::any& msg) {
                   m->transform.rotation.x, m->transform.rotation.y, m->transform.rotation.z, m->transform.rotation.w);
     return topic + ": " + mod_describe::header(m->header) + b;
   }
+  if (const moving_object_msgs::MovingObjectArray* m = std::any_cast<moving_object_msgs::MovingObjectArray>(&msg)) {
+    std::string out = topic + ": " + mod_describe::header(m->header);
+    std::snprintf(b, sizeof b, " objects=%zu\n", m->moving_object_array.size());
+    out += b;
+    for (const auto& o : m->moving_object_array) {
+      std::snprintf(b, sizeof b, "  id=%d center=(%a %a %a) q=(%g %g %g %g) bbox=(%a %a %a)\n", o.id, o.center.position.x,
+                    o.center.position.y, o.center.position.z, o.center.orientation.x, o.center.orientation.y,
+                    o.center.orientation.z, o.center.orientation.w, o.bounding_box.x, o.bounding_box.y, o.bounding_box.z);
+      out += b;
+      // the velocity is a member at the median SPEED (std::sort leaves ties unspecified): the speed is what is pinned
+      const float vx = (float)o.velocity.x, vy = (float)o.velocity.y, vz = (float)o.velocity.z;
+      std::snprintf(b, sizeof b, "  speed=%a\n", (double)std::sqrt((vx * vx + vy * vy) + vz * vz));
+      out += b;
+    }
+    return out;
+  }
   return topic + ": <unknown message type>\n";
 }
 
@@ -77,11 +94,14 @@ inline std::string render(const std::string& topic, const std::any& msg) {
 // subscribers: bit0 ~scene_flow, bit1 ~depth, bit2 ~synthetic_optical_flow, bit3 ~optical_flow.
 // finish(node) must wait for the node's construct() worker.  Returns 0, -11 on an exception, -12 when the log does
 // not fit; *shutdown_requested tells whether the node asked ros::shutdown().
-template <class Node, class Finish>
+// fused != 0: the private parameter ~fused_clusterer is set before the node is built (the product's node then runs the
+// clusterer in process; the reference's node does not know the parameter - its wrapper chains the reference's
+// clusterer nodelet behind ~scene_flow in `finish`).  setup(node) runs once after construction.
+template <class Node, class Setup, class Finish>
 int run(int w, int h, int n_frames, const camera* cam, float f, float T, float min_d, float max_d,
         const float* disparities, const float* flows, const double* motions, const int32_t* ok_flags,
-        const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff, Finish finish, char* log, int log_cap,
-        int32_t* shutdown_requested) {
+        const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff, int fused, Setup setup, Finish finish,
+        char* log, int log_cap, int32_t* shutdown_requested) {
   mod_ref_upstream::Script script;
   script.width = w; script.height = h;
   const size_t P = (size_t)w * h;
@@ -100,8 +120,11 @@ int run(int w, int h, int n_frames, const camera* cam, float f, float T, float m
   mod_ref_upstream::script() = &script;
   ros::mod_ref_pub_log() = &events;
   ros::mod_ref_shutdown_requested() = false;
+  ros::mod_ref_int_params().clear();
+  if (fused) ros::mod_ref_int_params().push_back({"fused_clusterer", 1});
   try {
     Node node;
+    setup(node);
     if (dynamic_flow_diff >= 0) {
       scene_flow_constructor::SceneFlowConstructorConfig cfg;
       cfg.dynamic_flow_diff = dynamic_flow_diff;
@@ -145,6 +168,7 @@ int run(int w, int h, int n_frames, const camera* cam, float f, float T, float m
   } catch (...) {
     rc = -11;
   }
+  ros::mod_ref_int_params().clear();
   mod_ref_upstream::script() = nullptr;
   ros::mod_ref_pub_log() = nullptr;
   if (shutdown_requested) *shutdown_requested = ros::mod_ref_shutdown_requested() ? 1 : 0;

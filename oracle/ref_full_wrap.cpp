@@ -426,13 +426,37 @@ int ref_bench_pipeline(int w, int h, const ref_camera* cam, float f, float T, fl
 int ref_node_sequence(int w, int h, int n_frames, const mod_node_sequence::camera* cam, float f, float T, float min_d,
                       float max_d, const float* disparities, const float* flows, const double* motions,
                       const int32_t* ok_flags, const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff,
-                      char* log, int log_cap, int32_t* shutdown_requested) {
-  auto finish = [](scene_flow_constructor::SceneFlowConstructor& node) {
+                      int fused, int32_t cluster_size, char* log, int log_cap, int32_t* shutdown_requested) {
+  // fused: the reference's TWO nodes chained the way the launch files wire them - every ~scene_flow cloud goes through
+  // ClustererNodelet::dataCB (only ~moving_objects subscribed), whose publication lands in the same log
+  std::unique_ptr<scene_flow_clusterer::ClustererNodelet> clusterer;
+  size_t seen = 0;
+  auto setup = [](scene_flow_constructor::SceneFlowConstructor&) {};
+  auto finish = [&](scene_flow_constructor::SceneFlowConstructor& node) {
     if (node.construct_thread_.joinable()) node.construct_thread_.join();
+    ros::PubLog* events = ros::mod_ref_pub_log();
+    if (!fused || !events) return;
+    std::vector<sensor_msgs::PointCloud2ConstPtr> clouds;
+    {
+      std::lock_guard<std::mutex> l(events->mu);
+      for (; seen < events->events.size(); seen++)
+        if (events->events[seen].topic == "scene_flow")
+          clouds.push_back(std::make_shared<sensor_msgs::PointCloud2>(
+              *std::any_cast<sensor_msgs::PointCloud2>(&events->events[seen].msg)));
+    }
+    for (const auto& cloud : clouds) {
+      if (!clusterer) {
+        clusterer.reset(new scene_flow_clusterer::ClustererNodelet());
+        prime_clusterer(*clusterer, cluster_size, 0.15, 0.3, 4, 1);
+      }
+      clusterer->dataCB(cloud);
+    }
+    std::lock_guard<std::mutex> l(events->mu);
+    seen = events->events.size();
   };
   return mod_node_sequence::run<scene_flow_constructor::SceneFlowConstructor>(
       w, h, n_frames, cam, f, T, min_d, max_d, disparities, flows, motions, ok_flags, stamps, subscribers,
-      dynamic_flow_diff, finish, log, log_cap, shutdown_requested);
+      dynamic_flow_diff, fused, setup, finish, log, log_cap, shutdown_requested);
 }
 
 }  // extern "C"

@@ -188,7 +188,7 @@ def bench_pipeline(disp_frames, prev_index, now_index, flows, cam, transforms, d
 
 
 def _node_sequence(fn, disps, flows, motions, ok_flags, stamps, cam, f, T, min_disparity, max_disparity, subscribers,
-                   dynamic_flow_diff, log_cap=1 << 16):
+                   dynamic_flow_diff, fused=False, cluster_size=2500, log_cap=1 << 16):
     """Shared marshalling of ref_node_sequence / rosb200_node_sequence (oracle/node_sequence.h)."""
     disps = np.ascontiguousarray(disps, np.float32)
     n, h, w = disps.shape
@@ -205,16 +205,17 @@ def _node_sequence(fn, disps, flows, motions, ok_flags, stamps, cam, f, T, min_d
     p = lambda a: C.c_void_p(a.ctypes.data)
     fn.restype = C.c_int
     rc = fn(w, h, n, C.byref(c), C.c_float(f), C.c_float(T), C.c_float(min_disparity), C.c_float(max_disparity),
-            p(disps), p(flows), p(motions), p(ok), p(st), C.c_int(subscribers), C.c_int32(dynamic_flow_diff), buf,
-            C.c_int(log_cap), C.byref(shut))
+            p(disps), p(flows), p(motions), p(ok), p(st), C.c_int(subscribers), C.c_int32(dynamic_flow_diff),
+            C.c_int(1 if fused else 0), C.c_int32(cluster_size), buf, C.c_int(log_cap), C.byref(shut))
     return dict(status=rc, log=buf.value.decode(), shutdown_requested=bool(shut.value))
 
 
 def node_sequence(disps, flows, motions, ok_flags, stamps, cam, f=1.0, T=1.0, min_disparity=0.0, max_disparity=128.0,
-                  subscribers=15, dynamic_flow_diff=-1):
-    """The reference NODE through SceneFlowConstructor::stereoCallback, one call per frame, with scripted upstream
+                  subscribers=15, dynamic_flow_diff=-1, fused=False, cluster_size=2500):
+    """fused: every ~scene_flow cloud is also handed to the reference's clusterer nodelet (the two-node chain).
+    The reference NODE through SceneFlowConstructor::stereoCallback, one call per frame, with scripted upstream
     estimators.  disps (n,H,W); flows (n,H,W,2), entry k = optical flow frame k-1 -> k (entry 0 unused); motions
     (n,4,4) libviso2 matrices previous -> current; ok_flags (n) bit0 disparity / bit1 motion / bit2 flow succeed;
     stamps (n,2) sec, nsec.  Returns dict(status, log, shutdown_requested); log = every publication and tf broadcast."""
     return _node_sequence(load().ref_node_sequence, disps, flows, motions, ok_flags, stamps, cam, f, T, min_disparity,
-                          max_disparity, subscribers, dynamic_flow_diff)
+                          max_disparity, subscribers, dynamic_flow_diff, fused, cluster_size)

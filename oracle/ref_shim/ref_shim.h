@@ -36,6 +36,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -249,7 +250,14 @@ class NodeHandle {
       if (kv.first == name) { v = kv.second; return true; }
     return false;
   }
-  template <class T, class U> bool param(const std::string&, T& v, const U& d) const { v = d; return false; }
+  template <class T, class U> bool param(const std::string& name, T& v, const U& d) const {
+    v = d;
+    if constexpr (std::is_same<T, bool>::value || std::is_same<T, int>::value) {  // a test may have set it (ints and flags)
+      for (const auto& kv : mod_ref_int_params())
+        if (kv.first == name) { v = static_cast<T>(kv.second); return true; }
+    }
+    return false;
+  }
   std::string resolveName(const std::string& n) const { return n; }
   template <class M> Publisher advertise(const std::string& topic, uint32_t) {
     Publisher p; p.state = std::make_shared<PubState>(); p.state->topic = topic; return p;

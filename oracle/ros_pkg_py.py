@@ -96,12 +96,12 @@ def cluster(points32, cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, nei
 
 
 def node_sequence(disps, flows, motions, ok_flags, stamps, cam, f=1.0, T=1.0, min_disparity=0.0, max_disparity=128.0,
-                  subscribers=15, dynamic_flow_diff=-1):
+                  subscribers=15, dynamic_flow_diff=-1, fused=False, cluster_size=2500):
     """The PRODUCT's constructor node (ros/scene_flow_constructor) through stereoCallback; arguments and result as
     ref_py.node_sequence."""
     from ref_py import _node_sequence
     return _node_sequence(load().rosb200_node_sequence, disps, flows, motions, ok_flags, stamps, cam, f, T,
-                          min_disparity, max_disparity, subscribers, dynamic_flow_diff)
+                          min_disparity, max_disparity, subscribers, dynamic_flow_diff, fused, cluster_size)
 
 
 def constructor_defaults():

@@ -229,13 +229,18 @@ int rosb200_cluster(int w, int h, const void* points32, int32_t cluster_size, do
 int rosb200_node_sequence(int w, int h, int n_frames, const mod_node_sequence::camera* cam, float f, float T, float min_d,
                           float max_d, const float* disparities, const float* flows, const double* motions,
                           const int32_t* ok_flags, const uint32_t* stamps, int subscribers, int32_t dynamic_flow_diff,
-                          char* log, int log_cap, int32_t* shutdown_requested) {
+                          int fused, int32_t cluster_size, char* log, int log_cap, int32_t* shutdown_requested) {
+  auto setup = [&](scene_flow_constructor::SceneFlowConstructor& node) {
+    if (!fused) return;
+    node.clusterer_config_.cluster_size = cluster_size;  // what a dynamic_reconfigure request on ~clusterer would set
+    node.moving_objects_pub_.state->num_subscribers = 1;
+  };
   auto finish = [](scene_flow_constructor::SceneFlowConstructor& node) {
     if (node.construct_job_.valid()) node.construct_job_.wait();
   };
   return mod_node_sequence::run<scene_flow_constructor::SceneFlowConstructor>(
       w, h, n_frames, cam, f, T, min_d, max_d, disparities, flows, motions, ok_flags, stamps, subscribers,
-      dynamic_flow_diff, finish, log, log_cap, shutdown_requested);
+      dynamic_flow_diff, fused, setup, finish, log, log_cap, shutdown_requested);
 }
 
 /* what the constructor node advertises and latches at start-up: out[0] = dynamic_flow_diff default, out[1] = number of

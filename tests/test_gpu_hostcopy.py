@@ -152,3 +152,21 @@ def test_previous_disparity_stays_resident_with_frame_ids(mod):
         c.set_frame_ids(60, 54)
         c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])
         assert c.resident_hits == 0
+
+
+def test_cluster_resident_equals_the_round_trip(mod):
+    """mod_cluster_resident on the cloud mod_scene_flow left on the device == mod_cluster on the downloaded cloud;
+    refused when there is no such cloud."""
+    from moving_object_detector_b200 import ClustererConfig, Context, ModError, synth
+    a = seq_inputs(synth.make_sequence(synth.CONFIGS["gazebo_640x480"], 2), 0)
+    h, w = a["now"].image.shape
+    with Context(w, h) as c:
+        with pytest.raises(ModError):
+            c.cluster_resident(w, h)
+        cloud = c.scene_flow(a["now"], a["prev"], a["flow"], a["cam"], a["prev2now"], a["dt_sec"])[0]
+        got = c.cluster_resident(w, h, ClustererConfig())
+        want = c.cluster(cloud, ClustererConfig())
+        assert got.n_objects == want.n_objects >= 2
+        assert got.labels.tobytes() == want.labels.tobytes() and got.objects.tobytes() == want.objects.tobytes()
+        with pytest.raises(ModError):   # mod_cluster replaced the resident cloud by the caller's
+            c.cluster_resident(w, h)

@@ -122,7 +122,8 @@ def test_if_the_reference_is_here_its_surface_is_the_same():
     ref_src = open(os.path.join(ref_dir, "src", "scene_flow_constructor.cpp")).read()
     src = open(os.path.join(PKG, "src", "scene_flow_constructor.cpp")).read()
     adv = lambda s: sorted(re.findall(r'advertise<([\w:]+)>\("(\w+)", (\d+)\)', s))
-    assert adv(src) == adv(ref_src)
+    # the reference's four topics, plus ~moving_objects of the optional in-process clusterer (~fused_clusterer)
+    assert [a for a in adv(src) if a[1] != "moving_objects"] == adv(ref_src)
 
 
 def test_node_latches_cfg_defaults_and_advertises_the_topics(plugin):
@@ -187,3 +188,52 @@ def test_gpu_node_publishes_what_the_reference_node_publishes(plugin, ref, scrip
     assert a["log"] == b["log"], "the nodes' publications differ:\n--- product\n%s\n--- reference\n%s" % (a["log"], b["log"])
     if subs == 15 and ok is None:
         assert a["log"].count("scene_flow: ") == script["n"] - 1
+
+
+# ---- ~fused_clusterer: the clusterer in the constructor's process -----------------------------------------------------
+def _objects_blocks(log):
+    """The moving_objects messages of a log, one string per message (header line + the objects' lines)."""
+    out, cur = [], None
+    for line in log.splitlines():
+        if line.startswith("moving_objects: "):
+            cur = [line]
+            out.append(cur)
+        elif cur is not None and line.startswith("  "):
+            cur.append(line)
+        else:
+            cur = None
+    return ["\n".join(b) for b in out]
+
+
+def test_reference_two_node_chain_over_a_sequence(ref, script):
+    """constructor -> ~scene_flow -> clusterer nodelet -> ~moving_objects with the reference's own nodes: what the
+    product's ~fused_clusterer option has to reproduce (and a check of the harness)."""
+    r = _run(ref, script, subscribers=1, fused=True, cluster_size=300)
+    assert r["status"] == 0
+    t = _frames(r["log"])
+    assert t[0] == ["/tf"] and all(t[k] == ["/tf", "scene_flow", "moving_objects"] for k in range(1, script["n"]))
+    blocks = _objects_blocks(r["log"])
+    assert len(blocks) == script["n"] - 1 and all("objects=2" in b for b in blocks)
+    assert "frame=left_camera_optical" in blocks[0]   # the header of the cloud, i.e. of the left image
+
+
+def test_fused_option_is_part_of_the_package():
+    src = open(os.path.join(PKG, "src", "scene_flow_constructor.cpp")).read()
+    assert 'param("fused_clusterer", fused_clusterer_, false)' in src
+    assert 'advertise<moving_object_msgs::MovingObjectArray>("moving_objects", 1)' in src
+    assert 'ros::NodeHandle(pnh, "clusterer")' in src
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ok", [None, [7, 7, 6, 7, 7], [7, 3, 7, 5, 7]])
+def test_gpu_fused_node_publishes_what_the_reference_two_node_chain_publishes(plugin, ref, script, ok):
+    want = _run(ref, script, ok=ok, subscribers=1, fused=True, cluster_size=300)
+    got = _run(plugin, script, ok=ok, subscribers=1, fused=True, cluster_size=300)
+    assert want["status"] == 0 and got["status"] == 0 and not got["shutdown_requested"]
+    assert got["log"] == want["log"], "publications differ:\n--- product\n%s\n--- reference\n%s" % (got["log"], want["log"])
+    # nobody subscribes to ~scene_flow: the cloud never leaves the GPU, the objects are the same
+    quiet = _run(plugin, script, ok=ok, subscribers=0, fused=True, cluster_size=300)
+    assert quiet["status"] == 0 and "scene_flow: " not in quiet["log"]
+    assert _objects_blocks(quiet["log"]) == _objects_blocks(want["log"])
+    if ok is None:
+        assert len(_objects_blocks(got["log"])) == script["n"] - 1
