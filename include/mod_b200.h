@@ -43,7 +43,8 @@ typedef enum {
                               /* up to max_objs (the reference's message array is unbounded)                       */
   MOD_ERR_INVALID_PARAM = -3, /* parameter value at which the reference itself throws / is undefined               */
                               /* (cluster_size == 0: cluster.at(0) on an empty cluster, clusterer_nodelet.cpp:174; */
-                              /*  neighbor_distance < 0)                                                           */
+                              /*  neighbor_distance < 0), or outside the dynamic_reconfigure range                 */
+                              /* (neighbor_distance > 10, cfg/Clusterer.cfg:11)                                    */
   MOD_ERR_CUDA = -4,          /* a CUDA runtime call failed; see mod_last_error()                                  */
   MOD_ERR_NO_DEVICE = -5,     /* no CUDA device / not compute capability 10.x                                      */
   MOD_ERR_CLUSTER_SLOTS = -6  /* more surviving clusters in one frame than the context's max_clusters              */
@@ -111,8 +112,9 @@ typedef struct {
 /* ---- context --------------------------------------------------------------------------------------------- */
 
 /* Creates a context on CUDA device `device` able to process frames up to max_w x max_h, max_batch frame pairs per
- * batched call and max_clusters surviving clusters per frame (0 = default 4096).  Owns device workspaces, one
- * stream and pinned staging.  Returns MOD_ERR_NO_DEVICE when there is no usable sm_100a GPU. */
+ * batched call and max_clusters surviving clusters per frame (0 = default 4096, at most 32768; a frame with more
+ * fails with MOD_ERR_CLUSTER_SLOTS and the caller re-creates the context with a larger value -- the host classes do).
+ * Owns device workspaces, one stream and pinned staging.  Returns MOD_ERR_NO_DEVICE when there is no usable sm_100a GPU. */
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx);
 void mod_destroy(mod_ctx* ctx);
 /* Message of the last error on this context ("" if none); valid until the next call on the context. */
@@ -189,6 +191,14 @@ int mod_cluster(mod_ctx* ctx, int w, int h, const void* points32, const mod_cl_p
 int mod_cluster_resident(mod_ctx* ctx, int w, int h, const mod_cl_params* params, int32_t* opt_labels,
                          mod_object* objs, int32_t max_objs, int32_t* n_objs);
 
+/* Counters of the frame the last mod_cluster / mod_cluster_resident / mod_pipeline call on this context processed:
+ * n_clusters is number_of_clusters_ after removeSmallClusters (clusterer_nodelet.cpp:354-393), which sizes the colour
+ * set of ~clusters and ~clusters_image (:269-322, color_set.cpp:16-26); n_objects counts the accepted MovingObjects
+ * (:176).  MOD_ERR_INVALID_ARG before the first such call. */
+int mod_last_frame_stats(const mod_ctx* ctx, mod_frame_stats* out);
+/* Surviving clusters per frame this context was created for (mod_create's max_clusters after defaulting / clamping). */
+int mod_max_clusters(const mod_ctx* ctx);
+
 /* ---- fused host entry: seam 1 + seam 2 with the cloud staying on the GPU ------------------------------------ */
 /* opt_out_points32 is only copied back when non-NULL (the reference publishes ~scene_flow only when it has
  * subscribers, scene_flow_constructor.cpp:141-142). */
@@ -211,8 +221,9 @@ int mod_scene_flow_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int bat
                                double dynamic_speed, void* d_points32, size_t frame_stride_points, uint8_t* d_mask,
                                float* d_opt_depth, float* d_opt_static_flow);
 
-/*  d_mask       : batch * w*h bytes as written by mod_scene_flow_batched_dev, or NULL to derive it from the cloud
- *                 (calculateDynamicMap, clusterer_nodelet.cpp:40-54).
+/*  d_points32   : 32-byte aligned (records are moved as 256-bit / 128-bit vectors), in both calls.
+ *  d_mask       : batch * w*h bytes as written by mod_scene_flow_batched_dev (16-byte aligned), or NULL to derive it
+ *                 from the cloud (calculateDynamicMap, clusterer_nodelet.cpp:40-54).
  *  d_opt_labels : batch * w*h int32 or NULL.
  *  d_objs       : batch * max_objs records; d_stats: batch records (n_objects, status per frame). */
 int mod_cluster_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, const void* d_points32,

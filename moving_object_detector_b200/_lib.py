@@ -87,6 +87,8 @@ PROTOTYPES = {
     "mod_last_error": (C.c_char_p, [C.c_void_p]),
     "mod_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mod_stream": (C.c_void_p, [C.c_void_p]),
+    "mod_last_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(FrameStats)]),
+    "mod_max_clusters": (C.c_int, [C.c_void_p]),
     "mod_set_static_flow_filter": (C.c_int, [C.c_void_p, C.c_int]),
     "mod_filter_fallbacks": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]),
     "mod_selfcheck_ddiv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -89,6 +89,7 @@ struct mod_ctx {
   mod_object* d_objs = nullptr;
   mod_frame_stats* d_fstats = nullptr;
   mod_frame_stats* h_fstats = nullptr;  // pinned
+  bool have_fstats = false;             // h_fstats holds the counters of a finished host-seam clusterer call
   HostStager stager;                    // pageable message buffers <-> device (hostcopy.cuh)
   // Frame identities for the host seams (mod_set_frame_ids): the disparity image uploaded as `now` stays on the device
   // and is reused when the next call names it as `prev` - in a stream every frame is uploaded once, as in the batched
@@ -98,11 +99,18 @@ struct mod_ctx {
   int resident_slot = 0, resident_w = 0, resident_h = 0;
   unsigned long long resident_hits = 0;
   int cloud_w = 0, cloud_h = 0;         // size of the cloud the last mod_scene_flow left in d_points (0: none)
-  // the clusterer's kernel sequence of the last small-batch call as an instantiated CUDA graph (run_cluster_dev)
-  cudaGraphExec_t cl_graph = nullptr;
-  ClLaunch cl_graph_L;
-  ClExtra cl_graph_X;
-  int cl_graph_launches = 0;
+  // the clusterer's kernel sequences of recent small-batch calls as instantiated CUDA graphs (run_cluster_dev), keyed
+  // on the launch descriptors; a few entries, because the streaming path alternates between two sets of buffers
+  struct ClGraph {
+    cudaGraphExec_t exec = nullptr;
+    ClLaunch L;
+    ClExtra X;
+    int launches = 0;
+    unsigned long long last_use = 0;
+  };
+  static constexpr int kClGraphs = 4;
+  ClGraph cl_graphs[kClGraphs];
+  unsigned long long cl_graph_clock = 0;
 
   // streaming buffers of mod_pipeline_sequence_host (lazily allocated)
   struct SeqBuf {
@@ -353,12 +361,17 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
     return fail(ctx, MOD_ERR_INVALID_PARAM, "cluster_size == 0: the reference throws std::out_of_range "
                 "(cluster.at(0) on an empty cluster, clusterer_nodelet.cpp:174)");
   if (params.neighbor_distance < 0) return fail(ctx, MOD_ERR_INVALID_PARAM, "neighbor_distance < 0");
+  if (params.neighbor_distance > kClMaxNeighborDistance)  // the tile kernels' halo and window arrays are sized for this
+    return fail(ctx, MOD_ERR_INVALID_PARAM, "neighbor_distance %d > %d (cfg/Clusterer.cfg:11 limits it to [1, 10])",
+                params.neighbor_distance, kClMaxNeighborDistance);
   if (max_objs < 0 || !d_objs || !d_stats) return fail(ctx, MOD_ERR_INVALID_ARG, "objs / stats missing");
   const size_t P = static_cast<size_t>(w) * h;
   if (P * static_cast<size_t>(batch) >= (1ull << 32))
     return fail(ctx, MOD_ERR_INVALID_ARG, "batch * w * h must stay below 2^32 pixels per call; split the batch");
   if (d_mask && (reinterpret_cast<uintptr_t>(d_mask) & 15u))
     return fail(ctx, MOD_ERR_INVALID_ARG, "d_mask must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(d_points) & 31u)  // records are read as two float4 halves / written as one 256-bit store
+    return fail(ctx, MOD_ERR_INVALID_ARG, "d_points32 must be 32-byte aligned");
   const float speed_thr = float_ceil_of_double(params.dynamic_speed);
   if (!d_mask) {
     MOD_CK(ctx, launch_dynamic_map(s, d_points, frame_stride_points, ctx->d_mask_own, w, h, batch, speed_thr));
@@ -414,11 +427,17 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
     ctx->launches += n_launches;
     return MOD_OK;
   }
-  if (!ctx->cl_graph || std::memcmp(&ctx->cl_graph_L, &L, sizeof(L)) != 0 ||
-      std::memcmp(&ctx->cl_graph_X, &X, sizeof(X)) != 0) {
-    if (ctx->cl_graph) {
-      cudaGraphExecDestroy(ctx->cl_graph);
-      ctx->cl_graph = nullptr;
+  mod_ctx::ClGraph* g = nullptr;
+  mod_ctx::ClGraph* victim = &ctx->cl_graphs[0];
+  for (auto& c : ctx->cl_graphs) {
+    if (c.exec && std::memcmp(&c.L, &L, sizeof(L)) == 0 && std::memcmp(&c.X, &X, sizeof(X)) == 0) g = &c;
+    if (c.last_use < victim->last_use) victim = &c;  // least recently used (unused entries carry 0)
+  }
+  if (!g) {
+    g = victim;
+    if (g->exec) {
+      cudaGraphExecDestroy(g->exec);
+      g->exec = nullptr;
     }
     MOD_CK(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     const cudaError_t launched = launch_cluster(s, L, X, &n_launches);
@@ -426,32 +445,38 @@ int run_cluster_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, const
     const cudaError_t ended = cudaStreamEndCapture(s, &graph);
     MOD_CK(ctx, launched);
     MOD_CK(ctx, ended);
-    const cudaError_t inst = cudaGraphInstantiate(&ctx->cl_graph, graph, 0);
+    const cudaError_t inst = cudaGraphInstantiate(&g->exec, graph, 0);
     cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) g->exec = nullptr;
     MOD_CK(ctx, inst);
-    ctx->cl_graph_L = L;
-    ctx->cl_graph_X = X;
-    ctx->cl_graph_launches = n_launches;
+    g->L = L;
+    g->X = X;
+    g->launches = n_launches;
   }
-  MOD_CK(ctx, cudaGraphLaunch(ctx->cl_graph, s));
-  ctx->launches += ctx->cl_graph_launches;
+  g->last_use = ++ctx->cl_graph_clock;
+  MOD_CK(ctx, cudaGraphLaunch(g->exec, s));
+  ctx->launches += g->launches;
   return MOD_OK;
 }
 
 int ensure_host_staging(mod_ctx* ctx) {
   if (ctx->host_ready) return MOD_OK;
   const size_t P = ctx->maxP;
-  MOD_CK(ctx, dev_alloc(&ctx->d_disp_now, P));
-  MOD_CK(ctx, dev_alloc(&ctx->d_disp_prev, P));
-  MOD_CK(ctx, dev_alloc(&ctx->d_flow, P * 2));
-  MOD_CK(ctx, dev_alloc(&ctx->d_points, P * 8));
-  MOD_CK(ctx, dev_alloc(&ctx->d_mask, P));
-  MOD_CK(ctx, dev_alloc(&ctx->d_labels, P));
-  MOD_CK(ctx, dev_alloc(&ctx->d_depth, P));
-  MOD_CK(ctx, dev_alloc(&ctx->d_static, P * 2));
-  MOD_CK(ctx, dev_alloc(&ctx->d_objs, static_cast<size_t>(ctx->max_clusters)));
-  MOD_CK(ctx, dev_alloc(&ctx->d_fstats, 1));
-  MOD_CK(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_fstats), sizeof(mod_frame_stats)));
+  // a call that failed half-way leaves its buffers in place: only the missing ones are allocated on the next attempt
+#define MOD_ENSURE(ptr, count) \
+  if (!(ptr)) MOD_CK(ctx, dev_alloc(&(ptr), (count)))
+  MOD_ENSURE(ctx->d_disp_now, P);
+  MOD_ENSURE(ctx->d_disp_prev, P);
+  MOD_ENSURE(ctx->d_flow, P * 2);
+  MOD_ENSURE(ctx->d_points, P * 8);
+  MOD_ENSURE(ctx->d_mask, P);
+  MOD_ENSURE(ctx->d_labels, P);
+  MOD_ENSURE(ctx->d_depth, P);
+  MOD_ENSURE(ctx->d_static, P * 2);
+  MOD_ENSURE(ctx->d_objs, static_cast<size_t>(ctx->max_clusters));
+  MOD_ENSURE(ctx->d_fstats, 1);
+#undef MOD_ENSURE
+  if (!ctx->h_fstats) MOD_CK(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_fstats), sizeof(mod_frame_stats)));
   ctx->host_ready = true;
   return MOD_OK;
 }
@@ -518,8 +543,10 @@ mod_pair_dev make_pair(const float* d_now, const float* d_prev, const float* d_f
 
 // Downloads objects + stats of one frame and converts the per-frame status into the return code.
 int fetch_objects(mod_ctx* ctx, cudaStream_t s, mod_object* objs, int32_t max_objs, int32_t* n_objs) {
+  ctx->have_fstats = false;
   MOD_CK(ctx, cudaMemcpyAsync(ctx->h_fstats, ctx->d_fstats, sizeof(mod_frame_stats), cudaMemcpyDeviceToHost, s));
   MOD_CK(ctx, cudaStreamSynchronize(s));
+  ctx->have_fstats = true;
   const mod_frame_stats fs = *ctx->h_fstats;
   if (n_objs) *n_objs = fs.n_objects;
   const int n_copy = fs.n_objects < max_objs ? fs.n_objects : max_objs;
@@ -610,6 +637,15 @@ int mod_filter_fallbacks(mod_ctx* ctx, int reset, unsigned long long* count) {
   return MOD_OK;
 }
 
+int mod_last_frame_stats(const mod_ctx* ctx, mod_frame_stats* out) {
+  if (!ctx || !out) return MOD_ERR_INVALID_ARG;
+  if (!ctx->h_fstats || !ctx->have_fstats) return MOD_ERR_INVALID_ARG;
+  *out = *ctx->h_fstats;
+  return MOD_OK;
+}
+
+int mod_max_clusters(const mod_ctx* ctx) { return ctx ? ctx->max_clusters : 0; }
+
 void* mod_stream(const mod_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
 
 int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters, mod_ctx** out_ctx) {
@@ -630,7 +666,7 @@ int mod_create(int device, int max_w, int max_h, int max_batch, int max_clusters
   ctx->max_w = max_w;
   ctx->max_h = max_h;
   ctx->max_batch = max_batch;
-  ctx->max_clusters = max_clusters == 0 ? 4096 : (max_clusters > 8192 ? 8192 : max_clusters);
+  ctx->max_clusters = max_clusters == 0 ? 4096 : (max_clusters > kClMaxClusters ? kClMaxClusters : max_clusters);
   ctx->maxP = static_cast<size_t>(max_w) * max_h;
   const size_t N = ctx->maxP * max_batch;
   const size_t C = static_cast<size_t>(ctx->max_clusters) * max_batch;
@@ -714,7 +750,8 @@ void mod_destroy(mod_ctx* ctx) {
     if (b.ev_comp) cudaEventDestroy(b.ev_comp);
     if (b.ev_out) cudaEventDestroy(b.ev_out);
   }
-  if (ctx->cl_graph) cudaGraphExecDestroy(ctx->cl_graph);
+  for (auto& c : ctx->cl_graphs)
+    if (c.exec) cudaGraphExecDestroy(c.exec);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -730,6 +767,7 @@ int mod_scene_flow(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_
   if (!cam || !now || !prev || !now->data || !prev->data || !flow_xy || !prev2now || !params)
     return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
   MOD_CK(ctx, cudaSetDevice(ctx->device));
+  ctx->cloud_w = ctx->cloud_h = 0;  // no resident cloud until this call has enqueued its kernel (mod_cluster_resident)
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
@@ -797,6 +835,7 @@ int mod_pipeline(mod_ctx* ctx, int w, int h, const mod_camera* cam, const mod_di
       max_objs < 0 || (max_objs > 0 && !objs))
     return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
   MOD_CK(ctx, cudaSetDevice(ctx->device));
+  ctx->cloud_w = ctx->cloud_h = 0;  // no resident cloud until this call has enqueued its kernel (mod_cluster_resident)
   if ((rc = ensure_host_staging(ctx)) != MOD_OK) return rc;
   cudaStream_t s = ctx->stream;
   const size_t P = static_cast<size_t>(w) * h;
@@ -827,6 +866,8 @@ int mod_scene_flow_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int bat
     return fail(ctx, MOD_ERR_INVALID_ARG, "bad size %dx%d batch %d", w, h, batch);
   if (!cam || !pairs || !params || !d_points32 || frame_stride_points < static_cast<size_t>(w) * h)
     return fail(ctx, MOD_ERR_INVALID_ARG, "null argument or frame stride smaller than a frame");
+  if (reinterpret_cast<uintptr_t>(d_points32) & 31u)  // one 256-bit store per record
+    return fail(ctx, MOD_ERR_INVALID_ARG, "d_points32 must be 32-byte aligned");
   MOD_CK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return run_scene_flow_dev(ctx, s, w, h, batch, *cam, pairs, *params, dynamic_speed, static_cast<float*>(d_points32),
@@ -973,15 +1014,15 @@ int mod_pipeline_sequence_host(mod_ctx* ctx, int w, int h, int n_frames, const m
   // small enough that upload / compute / download of neighbouring chunks overlap.
   int chunk = ctx->max_batch < 8 ? ctx->max_batch : 8;
   if (ctx->seq_chunk == 0) {
-    for (auto& b : ctx->seq) {
-      MOD_CK(ctx, dev_alloc(&b.d_disp, ctx->maxP * (chunk + 1)));
-      MOD_CK(ctx, dev_alloc(&b.d_flow, ctx->maxP * 2 * chunk));
-      MOD_CK(ctx, dev_alloc(&b.d_points, ctx->maxP * 8 * chunk));
-      MOD_CK(ctx, dev_alloc(&b.d_mask, ctx->maxP * chunk));
-      MOD_CK(ctx, dev_alloc(&b.d_stats, static_cast<size_t>(chunk)));
-      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_in, cudaEventDisableTiming));
-      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_comp, cudaEventDisableTiming));
-      MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_out, cudaEventDisableTiming));
+    for (auto& b : ctx->seq) {  // only what an earlier, failed attempt did not already allocate
+      if (!b.d_disp) MOD_CK(ctx, dev_alloc(&b.d_disp, ctx->maxP * (chunk + 1)));
+      if (!b.d_flow) MOD_CK(ctx, dev_alloc(&b.d_flow, ctx->maxP * 2 * chunk));
+      if (!b.d_points) MOD_CK(ctx, dev_alloc(&b.d_points, ctx->maxP * 8 * chunk));
+      if (!b.d_mask) MOD_CK(ctx, dev_alloc(&b.d_mask, ctx->maxP * chunk));
+      if (!b.d_stats) MOD_CK(ctx, dev_alloc(&b.d_stats, static_cast<size_t>(chunk)));
+      if (!b.ev_in) MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_in, cudaEventDisableTiming));
+      if (!b.ev_comp) MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_comp, cudaEventDisableTiming));
+      if (!b.ev_out) MOD_CK(ctx, cudaEventCreateWithFlags(&b.ev_out, cudaEventDisableTiming));
     }
     ctx->seq_chunk = chunk;
   }

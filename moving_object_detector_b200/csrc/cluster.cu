@@ -1645,8 +1645,13 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
   }
   cl_roots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
   cl_slots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
-  cl_rank_kernel<<<L.batch, kBlock, static_cast<size_t>(L.max_clusters) * sizeof(int), s>>>(L, X.work_count, X.work_items,
-                                                                                          X.member_offset);
+  const size_t rank_smem = static_cast<size_t>(L.max_clusters) * sizeof(int);
+  if (rank_smem > 48 * 1024) {  // contexts created for more than 12288 clusters per frame: opt in to the larger table
+    const cudaError_t e = cudaFuncSetAttribute(cl_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(rank_smem));
+    if (e != cudaSuccess) return e;
+  }
+  cl_rank_kernel<<<L.batch, kBlock, rank_smem, s>>>(L, X.work_count, X.work_items, X.member_offset);
   cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, X.list_speed, counters, X.member_offset, X.cursor, X.member_speed,
                                                  X.member_pixel);
   const bool clusters_possible = static_cast<size_t>(L.w) * L.h >= kObjClusterMinPixels;

@@ -60,6 +60,10 @@ struct SfLaunch {
   int first_frame;       // output frame index of pair[0]
 };
 
+constexpr int kClMaxNeighborDistance = 10;  // cfg/Clusterer.cfg:11 (neighbor_distance in [1, 10]); sizes the halos
+constexpr int kClMaxClusters = 32768;       // surviving clusters per frame a context can be created for (cl_rank's
+                                            // shared-memory key table: 128 KB)
+
 // Clusterer launch descriptor (one per batched call; every kernel grid-strides over the batch's flat pixel range).
 struct ClLaunch {
   const float* points;   // 8 floats per point

@@ -11,18 +11,29 @@ std::string ctxError(mod_ctx* ctx, const char* what, int rc) {
   return std::string(what) + " failed (" + std::to_string(rc) + "): " + (ctx ? mod_last_error(ctx) : "no context");
 }
 
-mod_ctx* createContext(int max_w, int max_h, int device) {
+mod_ctx* createContext(int max_w, int max_h, int device, int max_clusters = 0) {
   mod_ctx* ctx = nullptr;
-  const int rc = mod_create(device, max_w, max_h, 1, 0, &ctx);
+  const int rc = mod_create(device, max_w, max_h, 1, max_clusters, &ctx);
   if (rc != MOD_OK)
     throw std::runtime_error("mod_create failed (" + std::to_string(rc) +
                              "): no usable sm_100a GPU; this path has no CPU fallback");
   return ctx;
 }
 
-// identity of a disparity message for mod_set_frame_ids: its stamp in nanoseconds (0 = unknown, never reused)
-unsigned long long frameId(const stereo_msgs::DisparityImage& d) {
-  return static_cast<unsigned long long>(d.header.stamp.sec) * 1000000000ull + d.header.stamp.nsec;
+// The reference's MovingObjectArray is unbounded (clusterer_nodelet.cpp:324-343); a context holds max_clusters
+// survivors per frame.  When a frame has more (MOD_ERR_CLUSTER_SLOTS) the context is re-created with room for twice as
+// many and the caller repeats the frame.  Returns false when the context is already at the library's limit.
+bool growContext(mod_ctx*& ctx, int max_w, int max_h, int device) {
+  const int have = mod_max_clusters(ctx);
+  mod_ctx* bigger = nullptr;
+  if (mod_create(device, max_w, max_h, 1, have * 2, &bigger) != MOD_OK) return false;
+  if (mod_max_clusters(bigger) <= have) {
+    mod_destroy(bigger);
+    return false;
+  }
+  mod_destroy(ctx);
+  ctx = bigger;
+  return true;
 }
 
 // mod_object records -> MovingObjectArray: float -> float64 widening as in the reference's assignments
@@ -78,7 +89,7 @@ void fillImage(sensor_msgs::Image& img, const std_msgs::Header& header, uint32_t
 namespace scene_flow_constructor {
 
 SceneFlowConstructorB200::SceneFlowConstructorB200(int max_w, int max_h, int device)
-    : ctx_(createContext(max_w, max_h, device)) {}
+    : ctx_(createContext(max_w, max_h, device)), max_w_(max_w), max_h_(max_h), device_(device) {}
 
 SceneFlowConstructorB200::~SceneFlowConstructorB200() { mod_destroy(ctx_); }
 
@@ -145,7 +156,7 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
     const mod_disparity now = toC(*disparity_now);
     const mod_transform ident{0, 0, 0, 0, 0, 0, 1};
     const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
-    mod_set_frame_ids(ctx_, frameId(*disparity_now), frameId(*disparity_now));
+    resident_now_.reset();  // both slots are rewritten with this frame; nothing is promised for the next call
     const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &now,
                                   zero_flow_.data(), static_cast<int32_t>(w * 8), &ident, 1.0, &p, nullptr,
                                   reinterpret_cast<float*>(depth.data.data()), nullptr);
@@ -192,8 +203,15 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
   // (stamp_now - stamp_previous).toSec(), :162-164
   const double dt = (disparity_now->header.stamp - disparity_previous->header.stamp).toSec();
   const mod_sf_params p{dynamic_flow_diff_, max_color_velocity_};
-  // in a stream the previous disparity is the one the last call uploaded as `now`: it is still on the device
-  mod_set_frame_ids(ctx_, frameId(*disparity_now), frameId(*disparity_previous));
+  // In a stream the previous disparity is the message the last call uploaded as `now` (the reference's
+  // disparity_previous_ = disparity_now_, :398): it is still on the device.  Identity is the message OBJECT, not its
+  // stamp (stamps repeat when a bag loops or /clock resets): the last `now` message is kept alive here, so its address
+  // cannot be recycled, and every upload gets a fresh id.
+  const unsigned long long prev_id =
+      (resident_now_ && resident_now_.get() == disparity_previous.get()) ? resident_now_id_ : 0ull;
+  const unsigned long long now_id = ++frame_counter_;
+  mod_set_frame_ids(ctx_, now_id, prev_id);
+  resident_now_.reset();
   const int rc = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &prev,
                                 reinterpret_cast<const float*>(left_flow->data.data()),
                                 static_cast<int32_t>(left_flow->step), &tr, dt, &p,
@@ -204,22 +222,35 @@ bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs
     last_error_ = ctxError(ctx_, "mod_scene_flow", rc);
     return false;
   }
+  resident_now_ = disparity_now;
+  resident_now_id_ = now_id;
   if (want_depth) depth_pub_.publish(depth);
   if (want_cloud) pc_with_velocity_pub_.publish(cloud);
   if (want_static) static_flow_pub_.publish(static_flow);
   if (moving_objects_pub_.getNumSubscribers() > 0) {  // the clusterer, in process, on the cloud still on the GPU
     const mod_cl_params cp{clusterer_cluster_size, clusterer_depth_diff, clusterer_dynamic_speed,
                            clusterer_neighbor_distance};
-    std::vector<mod_object> objs(4096);
+    objs_.resize(static_cast<size_t>(mod_max_clusters(ctx_)));
     int32_t n = 0;
-    const int rc2 = mod_cluster_resident(ctx_, static_cast<int>(w), static_cast<int>(h), &cp, nullptr, objs.data(),
-                                         static_cast<int32_t>(objs.size()), &n);
+    int rc2 = mod_cluster_resident(ctx_, static_cast<int>(w), static_cast<int>(h), &cp, nullptr, objs_.data(),
+                                   static_cast<int32_t>(objs_.size()), &n);
+    while (rc2 == MOD_ERR_CLUSTER_SLOTS && growContext(ctx_, max_w_, max_h_, device_)) {
+      // more surviving clusters than the context had room for: the new context recomputes this frame's cloud
+      resident_now_.reset();
+      objs_.resize(static_cast<size_t>(mod_max_clusters(ctx_)));
+      rc2 = mod_scene_flow(ctx_, static_cast<int>(w), static_cast<int>(h), &camera_, &now, &prev,
+                           reinterpret_cast<const float*>(left_flow->data.data()), static_cast<int32_t>(left_flow->step),
+                           &tr, dt, &p, nullptr, nullptr, nullptr);
+      if (rc2 == MOD_OK)
+        rc2 = mod_cluster_resident(ctx_, static_cast<int>(w), static_cast<int>(h), &cp, nullptr, objs_.data(),
+                                   static_cast<int32_t>(objs_.size()), &n);
+    }
     if (rc2 != MOD_OK) {
       last_error_ = ctxError(ctx_, "mod_cluster_resident", rc2);
       return true;  // the scene flow itself was computed and published
     }
     moving_object_msgs::MovingObjectArray out;
-    fillMovingObjects(objs.data(), n, left_flow->header, out);  // the header ~scene_flow carries
+    fillMovingObjects(objs_.data(), n, left_flow->header, out);  // the header ~scene_flow carries
     moving_objects_pub_.publish(out);
   }
   return true;
@@ -270,7 +301,8 @@ void repackVelocityCloud(const sensor_msgs::PointCloud2& msg, std::vector<uint8_
   }
 }
 
-ClustererB200::ClustererB200(int max_w, int max_h, int device) : ctx_(createContext(max_w, max_h, device)) {}
+ClustererB200::ClustererB200(int max_w, int max_h, int device)
+    : ctx_(createContext(max_w, max_h, device)), max_w_(max_w), max_h_(max_h), device_(device) {}
 ClustererB200::~ClustererB200() { mod_destroy(ctx_); }
 
 void ClustererB200::reconfigureCB(const ClustererConfig& config, uint32_t /*level*/) {
@@ -297,19 +329,26 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
   if (layout == 0) repackVelocityCloud(msg, repacked);
   const uint8_t* cloud = layout == 1 ? msg.data.data() : repacked.data();
   const mod_cl_params p{cluster_size_th_, depth_diff_th_, dynamic_speed_th_, neighbor_distance_th_};
-  std::vector<mod_object> objs(4096);
+  std::vector<mod_object>& objs = objs_;
   int32_t n = 0;
   const size_t n_points = static_cast<size_t>(msg.width) * msg.height;
   std::vector<int32_t> labels;  // cluster_map_ after removeSmallClusters; only the visualisations need it on the host
   if (want_markers || want_image) labels.resize(n_points);
-  const int rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), cloud, &p,
-                             labels.empty() ? nullptr : labels.data(), objs.data(), static_cast<int32_t>(objs.size()), &n);
+  int rc;
+  do {  // the reference's object array is unbounded: a frame with more survivors than the context holds is repeated
+        // on a context with room for twice as many
+    objs.resize(static_cast<size_t>(mod_max_clusters(ctx_)));
+    rc = mod_cluster(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), cloud, &p,
+                     labels.empty() ? nullptr : labels.data(), objs.data(), static_cast<int32_t>(objs.size()), &n);
+  } while (rc == MOD_ERR_CLUSTER_SLOTS && growContext(ctx_, max_w_, max_h_, device_));
   if (rc != MOD_OK) {
     last_error_ = ctxError(ctx_, "mod_cluster", rc);
     return false;
   }
-  // number_of_clusters_ after removeSmallClusters == clusters.size(); every survivor is accepted as an object (all
-  // its members satisfy |v| >= dynamic_speed, so does the median), hence n is that count.
+  // number_of_clusters_ after removeSmallClusters (clusterer_nodelet.cpp:354-393) sizes the colour set of both
+  // visualisations (:269-322); n counts the MovingObjects accepted at :176
+  mod_frame_stats fs{};
+  const int n_clusters = mod_last_frame_stats(ctx_, &fs) == MOD_OK ? fs.n_clusters : n;
   if (want_markers) {  // publishClusters :269-291, cluster2Marker :119-145
     uint8_t table[768];
     mod_host_hsv_colormap(table);
@@ -317,10 +356,10 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
     visualization_msgs::Marker delete_marker;
     delete_marker.action = visualization_msgs::Marker::DELETEALL;
     clusters_msg.markers.push_back(delete_marker);
-    clusters_msg.markers.resize(static_cast<size_t>(n) + 1);
-    for (int32_t id = 0; id < n; id++) {
+    clusters_msg.markers.resize(static_cast<size_t>(n_clusters) + 1);
+    for (int32_t id = 0; id < n_clusters; id++) {
       visualization_msgs::Marker& m = clusters_msg.markers[static_cast<size_t>(id) + 1];
-      const uint8_t* bgr = table + 3 * (id * 255 / n);  // ColorSet::resize(clusters.size()), color_set.cpp:21-25
+      const uint8_t* bgr = table + 3 * (id * 255 / n_clusters);  // ColorSet::resize(clusters.size()), color_set.cpp:21-25
       m.header = msg.header;
       m.id = id;
       m.type = visualization_msgs::Marker::POINTS;
@@ -339,7 +378,7 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
       for (uint32_t v = 0; v < msg.height; v++) {
         const size_t i = static_cast<size_t>(msg.width) * v + u;
         const int32_t c = labels[i];
-        if (c < 0 || c >= n) continue;
+        if (c < 0 || c >= n_clusters) continue;
         geometry_msgs::Point pt;
         pt.x = pts[8 * i];
         pt.y = pts[8 * i + 1];
@@ -359,8 +398,8 @@ bool ClustererB200::dataCB(const sensor_msgs::PointCloud2& msg) {
     image.is_bigendian = 0;
     image.step = msg.width * 3;
     image.data.resize(n_points * 3);
-    const int rc2 = mod_clusters_image(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), labels.data(), n,
-                                       image.data.data());
+    const int rc2 = mod_clusters_image(ctx_, static_cast<int>(msg.width), static_cast<int>(msg.height), labels.data(),
+                                       n_clusters, image.data.data());
     if (rc2 != MOD_OK) {
       last_error_ = ctxError(ctx_, "mod_clusters_image", rc2);
       return false;

@@ -102,6 +102,11 @@ class SceneFlowConstructorB200 {
   sensor_msgs::PointCloud2 cloud_msg_;
   sensor_msgs::Image depth_msg_, static_flow_msg_;
   std::vector<float> zero_flow_;
+  std::vector<mod_object> objs_;
+  int max_w_ = 0, max_h_ = 0, device_ = 0;
+  // the disparity message whose image the last call left on the device as `now`, and the id it was uploaded under
+  std::shared_ptr<const stereo_msgs::DisparityImage> resident_now_;
+  unsigned long long resident_now_id_ = 0, frame_counter_ = 0;
 };
 
 // pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZVelocity>) layout (pcl_point_xyz_velocity.h:8-34): fills everything
@@ -157,6 +162,8 @@ class ClustererB200 {
   double dynamic_speed_th_ = 0.3;
   int neighbor_distance_th_ = 4;
   std::string last_error_;
+  std::vector<mod_object> objs_;
+  int max_w_ = 0, max_h_ = 0, device_ = 0;
 };
 
 }  // namespace scene_flow_clusterer

@@ -192,6 +192,10 @@ def test_capacity_and_parameter_errors(oracle):
         with pytest.raises(ModError) as e:
             c.cluster(cloud, ClustererConfig(neighbor_distance=-1))
         assert e.value.status == _lib.MOD_ERR_INVALID_PARAM
+        # beyond the dynamic_reconfigure range [1, 10] (cfg/Clusterer.cfg:11) the halo arrays would overflow: an error
+        with pytest.raises(ModError) as e:
+            c.cluster(cloud, ClustererConfig(neighbor_distance=11))
+        assert e.value.status == _lib.MOD_ERR_INVALID_PARAM
         # a negative cluster_size removes everything (size_t comparison, clusterer_nodelet.cpp:374)
         got = c.cluster(cloud, ClustererConfig(cluster_size=-1))
         assert got.n_objects == 0 and (got.labels == -1).all()

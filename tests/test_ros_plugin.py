@@ -47,6 +47,8 @@ def test_package_surface_matches_the_reference_contract():
         assert topic in src
     node = open(os.path.join(PKG, "src", "clusterer_node.cpp")).read()
     assert '"scene_flow_clusterer/scene_flow_clusterer"' in node
+    # the reference's wrapper (clusterer_node.cpp:8-13): no load / unload services, no remappings forwarded
+    assert "loader(false)" in node and "getRemappings" not in node
 
 
 def test_if_the_reference_is_here_its_surface_is_the_same():
