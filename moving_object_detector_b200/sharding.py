@@ -5,7 +5,8 @@ A frame pair (disp_prev, disp_now, flow, transform, dt) -> (cloud, mask, labels,
 input), so a batch is split into CONTIGUOUS blocks of pairs, one block per rank: inside a block disp_prev of pair
 i+1 is disp_now of pair i, so only one boundary frame per rank is duplicated.  Pixel data never leaves its GPU; the
 only collective is an all-gather of the fixed-size per-frame MovingObject records and frame stats (NCCL on GPUs,
-gloo in the CPU tests) -- the analogue of every constructor/clusterer pair publishing ~moving_objects to one tracker.
+gloo in the CPU tests), once per batch of steps -- the analogue of every constructor/clusterer pair publishing
+~moving_objects to one tracker.
 """
 from __future__ import annotations
 
@@ -50,43 +51,62 @@ def gather_object_lists(objs, stats, group=None):
 
 
 class ObjectListGatherer:
-    """The per-step collective of the data-parallel path with its buffers allocated once.
+    """The collective of the data-parallel path with its buffers allocated once.
 
-    `objs` (block, objs_bytes) and `stats` (block, stats_bytes) are uint8 views into ONE flat send buffer, so that a
-    single all-gather moves both; the clusterer writes into them through their device pointers.  On CUDA the
-    collective runs on a side stream: launch() orders it after everything already enqueued on the current stream,
-    the next step's scene-flow kernel overlaps it, and wait() must be called (on the current stream) before the send
-    buffers are overwritten and before results are read.  On CPU tensors (gloo, tests) everything is synchronous.
+    The send buffer is a ring of `ring` step slots; slot k holds the records one step's clusterer call wrote:
+    `slot(k)` = (objs (block, objs_bytes), stats (block, stats_bytes)) uint8 views the clusterer writes into through
+    their device pointers.  ONE all-gather moves the first `slots` ring entries of every rank (launch(slots)), so a
+    stream of steps pays one collective per ring, not one per step: NCCL's CTAs spin on their peers while they hold SM
+    slots, and a per-step collective overlapping the next step's kernels made every rank pay the slowest rank's tail
+    (round 1: -6 % at eight GPUs).  On CUDA the collective runs on a side stream: launch() orders it after everything
+    already enqueued on the current stream, later work overlaps it, and wait() must be called (on the current stream)
+    before a send slot is overwritten and before results are read.  On CPU tensors (gloo, tests) everything is
+    synchronous.  `objs` / `stats` are slot 0 (the one-slot form the tests and small drivers use).
     """
 
-    def __init__(self, block: int, objs_bytes: int, stats_bytes: int, device, group=None):
+    def __init__(self, block: int, objs_bytes: int, stats_bytes: int, device, group=None, ring: int = 1):
         import torch
         import torch.distributed as dist
         self.group = group
         self.world = dist.get_world_size(group)
-        self.block, self.objs_bytes, self.stats_bytes = block, objs_bytes, stats_bytes
-        n = block * (objs_bytes + stats_bytes)
-        self._send = torch.zeros(n, dtype=torch.uint8, device=device)
-        self._recv = torch.zeros(self.world * n, dtype=torch.uint8, device=device)
-        self.objs = self._send[:block * objs_bytes].view(block, objs_bytes)
-        self.stats = self._send[block * objs_bytes:].view(block, stats_bytes)
+        self.block, self.objs_bytes, self.stats_bytes, self.ring = block, objs_bytes, stats_bytes, ring
+        self.slot_bytes = block * (objs_bytes + stats_bytes)
+        self._send = torch.zeros(ring * self.slot_bytes, dtype=torch.uint8, device=device)
+        self._recv = torch.zeros(self.world * ring * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.objs, self.stats = self.slot(0)
         self._cuda = self._send.is_cuda
         if self._cuda:
             self._side = torch.cuda.Stream(device=device)
             self._ready = torch.cuda.Event()
             self._done = torch.cuda.Event()
         self._pending = False
+        self._slots = ring
+        self.launches = 0
 
-    def launch(self):
+    def slot(self, k: int):
+        """(objs, stats) views of ring slot k of the send buffer."""
+        base = k * self.slot_bytes
+        split = base + self.block * self.objs_bytes
+        return (self._send[base:split].view(self.block, self.objs_bytes),
+                self._send[split:base + self.slot_bytes].view(self.block, self.stats_bytes))
+
+    def launch(self, slots: int = None):
+        """All-gathers ring slots [0, slots) (default: the whole ring) of every rank."""
         import torch
         import torch.distributed as dist
+        slots = self.ring if slots is None else slots
+        assert 1 <= slots <= self.ring
+        self._slots = slots
+        n = slots * self.slot_bytes
+        send, recv = self._send[:n], self._recv[:self.world * n]
+        self.launches += 1
         if not self._cuda:
-            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
             return
         self._ready.record()
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._ready)
-            dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
             self._done.record()
         self._pending = True
 
@@ -97,12 +117,15 @@ class ObjectListGatherer:
             torch.cuda.current_stream().wait_event(self._done)
             self._pending = False
 
-    def result(self):
-        """(world, block, objs_bytes) and (world, block, stats_bytes) views of the gathered buffer; call wait() first."""
-        per = self._recv.view(self.world, -1)
+    def result(self, slot: int = 0):
+        """(world, block, objs_bytes) and (world, block, stats_bytes) views of ring slot `slot` of the last gather;
+        call wait() first."""
+        assert 0 <= slot < self._slots
+        per = self._recv[:self.world * self._slots * self.slot_bytes].view(self.world, self._slots, self.slot_bytes)
+        one = per[:, slot]
         split = self.block * self.objs_bytes
-        return (per[:, :split].reshape(self.world, self.block, self.objs_bytes),
-                per[:, split:].reshape(self.world, self.block, self.stats_bytes))
+        return (one[:, :split].reshape(self.world, self.block, self.objs_bytes),
+                one[:, split:].reshape(self.world, self.block, self.stats_bytes))
 
 
 def merge_gathered(g_objs: np.ndarray, g_stats: np.ndarray, n_pairs: int, obj_dtype, stats_dtype) -> List[np.ndarray]:

@@ -87,6 +87,27 @@ def _worker(rank, world, port, n_pairs, q):
         gat.wait()
         o2, s2 = gat.result()
         ok &= bool(torch.equal(o2, g_objs) and torch.equal(s2, g_stats))
+        # a ring of three step slots gathered by ONE collective (a stream of steps, one gather per batch); slot k
+        # carries the records with every id shifted by k, and a partial ring (two of three slots) gathers a prefix
+        ring = ObjectListGatherer(t_objs.shape[0], t_objs.shape[1], t_stats.shape[1], "cpu", ring=3)
+        for slots in (3, 2):
+            for k in range(slots):
+                o, st = ring.slot(k)
+                shifted = objs.copy()
+                shifted["id"] += k
+                o.copy_(torch.from_numpy(shifted.view(np.uint8).reshape(objs.shape[0], -1).copy()))
+                st.copy_(t_stats)
+            before = ring.launches
+            ring.launch(slots)
+            ring.wait()
+            ok &= ring.launches == before + 1
+            for k in range(slots):
+                ok_o, ok_s = ring.result(k)
+                ok &= bool(torch.equal(ok_s, g_stats))
+                for r in range(world):
+                    want = _rank_records(r, world, n_pairs)[0]
+                    want["id"] += k
+                    ok &= bool(np.array_equal(ok_o[r].numpy().tobytes(), want.tobytes()))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
