@@ -500,6 +500,9 @@ __global__ void __launch_bounds__(kBlock)
 #ifndef CL_TILE_MIN_BLOCKS
 #define CL_TILE_MIN_BLOCKS 8
 #endif
+#ifndef CL_TILE_CMP_ROWS
+#define CL_TILE_CMP_ROWS 4  // pixel rows per pass of the label-compare stencil (4: 0.558 ms, 2: 0.565, 1: 0.564, list walk 0.568)
+#endif
 template <int NC>
 __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
     cl_tile_fast_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
@@ -810,6 +813,7 @@ __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
   const bool skip_compare = false;
 #endif
   bool unioned = false;
+#ifdef CL_TILE_LIST_COMPARE
   for (int e0 = 0; e0 < (skip_compare ? 0 : nd); e0 += kBlock) {  // C2b: whatever still differs
     const int e = e0 + threadIdx.x;
     int c = 0;
@@ -828,6 +832,60 @@ __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
       __syncwarp();
     }
   }
+#else
+  // C2b: whatever still differs.  This pass is a stencil over the label image, not a list walk: a warp takes the tile's
+  // rows kCmpRows at a time with one COLUMN per lane, holds the label rows it needs in registers, and obtains the
+  // label of the neighbour at (dx, dy) as row -dy shifted by dx lanes (one warp shuffle per label row and dx, shared by
+  // the kCmpRows pixel rows), so an accepted edge costs a compare instead of a shared-memory load behind a bit test.
+  // (ncu, r01: the list form of this pass was 17 % of the kernel's instructions.)
+  if (!skip_compare) {
+    constexpr int kWarpRows = kTileH / (kBlock / 32);  // 4 rows of the tile per warp
+    constexpr int kCmpRows = CL_TILE_CMP_ROWS;
+    static_assert(kWarpRows % kCmpRows == 0, "rows per pass must divide the warp's rows");
+    const int warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int pass = 0; pass < kWarpRows / kCmpRows; pass++) {
+      const int r0 = warp * kWarpRows + pass * kCmpRows;  // first pixel row of this pass
+      int lr[kCmpRows + NC];                              // labels of rows r0 - NC .. r0 + kCmpRows - 1, this column
+#pragma unroll
+      for (int j = 0; j < kCmpRows + NC; j++) {
+        const int rr = r0 - NC + j;
+        lr[j] = rr >= 0 ? s_lab[rr * SW + lane] : -1;  // non-dynamic pixels hold stale values: never selected below
+      }
+      uint32_t diff[kCmpRows];
+#pragma unroll
+      for (int q = 0; q < kCmpRows; q++) diff[q] = 0u;
+#pragma unroll
+      for (int j = 0; j < kCmpRows + NC; j++) {
+#pragma unroll
+        for (int dx = 0; dx <= NC; dx++) {
+          // lanes < dx read a wrapped-around column: those cells lie outside the tile and are not in s_E
+          const int v = dx == 0 ? lr[j] : __shfl_sync(kFull, lr[j], (lane - dx) & 31);
+#pragma unroll
+          for (int q = 0; q < kCmpRows; q++) {
+            const int dy = q + NC - j;
+            if (dy < 0 || dy > NC || (dx == 0 && dy == 0)) continue;
+            if (v != lr[q + NC]) diff[q] |= 1u << ((NC - dy) * S + (NC - dx));
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kCmpRows; q++) {
+        const int c = (r0 + q) * SW + lane;
+        uint32_t d = (s_m[c + kCore] & kDyn) ? (diff[q] & s_E[c]) : 0u;
+        unioned = unioned || d != 0;
+        while (__any_sync(kFull, d != 0)) {
+          if (d) {
+            const int k = __ffs(d) - 1;
+            d &= d - 1;
+            smem_union(s_lab, c, c + cell_offset(k));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+#endif
   const bool reflatten = __syncthreads_or(unioned);  // labels are flat unless C2b still had to union
 
   // D1: flatten the tile-local forest; roots initialise their partial record
