@@ -1286,6 +1286,120 @@ __device__ __forceinline__ bool objects_use_clusters(const ClLaunch& L, int n_wo
   return s_max_members >= kObjClusterMinMembers;
 }
 
+// ---- member-list passes shared by the two cl_objects kernels ---------------------------------------------------------
+// A cluster's member list is walked three (radix passes) plus one (tie-break) times.  Lists that do not fit the shared
+// memory staging stream from global memory (L2: cl_scatter has just written them), and a pass over a 30 k list by 1024
+// threads is only a handful of iterations, so its time is load latency, not bandwidth: the streaming form reads the
+// list as 16-byte vectors, two in flight per thread (eight members), after a scalar head that aligns the pointer.
+__device__ __forceinline__ void obj_count(unsigned* hist, uint32_t v, bool ok, uint32_t himask, uint32_t prefix, int shift,
+                                          uint32_t binmask, int lane) {
+  int bin = -1;
+  if (ok && (v & himask) == prefix) bin = static_cast<int>((v >> shift) & binmask);
+  // members of one object move alike: in the first pass nearly every warp is uniform (one atomic per warp);
+  // later passes spread over the bins and plain shared-memory atomics are cheaper than a match
+  int uniform;
+  __match_all_sync(kFull, bin, &uniform);
+  if (uniform) {
+    if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
+  } else if (bin >= 0) {
+    atomicAdd(&hist[bin], 1u);
+  }
+}
+
+// head / vector split of a global list of n 32-bit entries: [0, head) scalar, nvec uint4 from head, then a scalar tail
+struct ObjSplit {
+  int head, nvec, tail0;
+};
+__device__ __forceinline__ ObjSplit obj_split(const void* p, int n) {
+  ObjSplit sp;
+  sp.head = min(n, static_cast<int>((4u - ((reinterpret_cast<uintptr_t>(p) >> 2) & 3u)) & 3u));
+  sp.nvec = (n - sp.head) >> 2;
+  sp.tail0 = sp.head + 4 * sp.nvec;
+  return sp;
+}
+
+// One histogram pass over the list (every thread of the CTA calls it: the match in obj_count is warp-wide).
+template <int kThreads>
+__device__ __forceinline__ void obj_hist_pass(unsigned* hist, const uint32_t* speeds, int n, bool in_global,
+                                              uint32_t himask, uint32_t prefix, int shift, uint32_t binmask) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (!in_global) {  // staged in shared memory
+    for (int j0 = 0; j0 < n; j0 += 4 * kThreads) {
+      uint32_t v[4];
+      bool ok[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int j = j0 + q * kThreads + tid;
+        ok[q] = j < n;
+        v[q] = ok[q] ? speeds[j] : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) obj_count(hist, v[q], ok[q], himask, prefix, shift, binmask, lane);
+    }
+    return;
+  }
+  const ObjSplit sp = obj_split(speeds, n);
+  {  // the at most three entries before and after the aligned body, one thread each
+    int j = -1;
+    if (tid < sp.head) j = tid;
+    else if (tid - sp.head < n - sp.tail0) j = sp.tail0 + (tid - sp.head);
+    obj_count(hist, j >= 0 ? __ldcg(speeds + j) : 0u, j >= 0, himask, prefix, shift, binmask, lane);
+  }
+  const uint4* vec = reinterpret_cast<const uint4*>(speeds + sp.head);
+  for (int i0 = 0; i0 < sp.nvec; i0 += 2 * kThreads) {
+    const int ia = i0 + tid, ib = ia + kThreads;
+    const bool oka = ia < sp.nvec, okb = ib < sp.nvec;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (oka) a = __ldcg(vec + ia);
+    if (okb) b = __ldcg(vec + ib);
+    obj_count(hist, a.x, oka, himask, prefix, shift, binmask, lane);
+    obj_count(hist, a.y, oka, himask, prefix, shift, binmask, lane);
+    obj_count(hist, a.z, oka, himask, prefix, shift, binmask, lane);
+    obj_count(hist, a.w, oka, himask, prefix, shift, binmask, lane);
+    obj_count(hist, b.x, okb, himask, prefix, shift, binmask, lane);
+    obj_count(hist, b.y, okb, himask, prefix, shift, binmask, lane);
+    obj_count(hist, b.z, okb, himask, prefix, shift, binmask, lane);
+    obj_count(hist, b.w, okb, himask, prefix, shift, binmask, lane);
+  }
+}
+
+// Smallest pixel index among the members whose speed equals `target` (this thread's share; 0x7fffffff if none).
+template <int kThreads>
+__device__ __forceinline__ int obj_tie_break(const uint32_t* speeds, const int* pixels, int n, bool in_global,
+                                             uint32_t target) {
+  const int tid = threadIdx.x;
+  int best = 0x7fffffff;
+  if (!in_global) {
+    for (int j = tid; j < n; j += kThreads)
+      if (speeds[j] == target) best = min(best, pixels[j]);
+    return best;
+  }
+  const ObjSplit sp = obj_split(speeds, n);
+  {
+    int j = -1;
+    if (tid < sp.head) j = tid;
+    else if (tid - sp.head < n - sp.tail0) j = sp.tail0 + (tid - sp.head);
+    if (j >= 0 && __ldcg(speeds + j) == target) best = min(best, pixels[j]);
+  }
+  const uint4* vec = reinterpret_cast<const uint4*>(speeds + sp.head);
+  for (int i0 = 0; i0 < sp.nvec; i0 += 2 * kThreads) {
+    const int ia = i0 + tid, ib = ia + kThreads;
+    uint4 a = make_uint4(~target, ~target, ~target, ~target), b = a;
+    if (ia < sp.nvec) a = __ldcg(vec + ia);
+    if (ib < sp.nvec) b = __ldcg(vec + ib);
+    const int ja = sp.head + 4 * ia, jb = sp.head + 4 * ib;
+    if (a.x == target) best = min(best, pixels[ja]);
+    if (a.y == target) best = min(best, pixels[ja + 1]);
+    if (a.z == target) best = min(best, pixels[ja + 2]);
+    if (a.w == target) best = min(best, pixels[ja + 3]);
+    if (b.x == target) best = min(best, pixels[jb]);
+    if (b.y == target) best = min(best, pixels[jb + 1]);
+    if (b.z == target) best = min(best, pixels[jb + 2]);
+    if (b.w == target) best = min(best, pixels[jb + 3]);
+  }
+  return best;
+}
+
 template <bool kClustersPossible>  // false: the instantiation small frames run never looks at the choice
 __global__ void __launch_bounds__(kObjBlock, 2)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
@@ -1334,30 +1448,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       const uint32_t prefix = s_prefix;
       const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
       const uint32_t binmask = (1u << bits) - 1u;
-      for (int j0 = 0; j0 < n; j0 += 4 * kObjBlock) {
-        uint32_t v[4];
-        bool ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int j = j0 + q * kObjBlock + threadIdx.x;
-          ok[q] = j < n;
-          v[q] = ok[q] ? speeds[j] : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          int bin = -1;
-          if (ok[q] && (v[q] & himask) == prefix) bin = static_cast<int>((v[q] >> shift) & binmask);
-          // members of one object move alike: in the first pass nearly every warp is uniform (one atomic per warp);
-          // later passes spread over the bins and plain shared-memory atomics are cheaper than a match
-          int uniform;
-          __match_all_sync(kFull, bin, &uniform);
-          if (uniform) {
-            if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
-          } else if (bin >= 0) {
-            atomicAdd(&hist[bin], 1u);
-          }
-        }
-      }
+      obj_hist_pass<kObjBlock>(hist, speeds, n, !staged, himask, prefix, shift, binmask);
       __syncthreads();
       // parallel suffix scan: thread t owns bins hi = kBins-1-2t and hi-1 (descending order, k counts from the top)
       const int hi = kBins - 1 - 2 * static_cast<int>(threadIdx.x);
@@ -1395,9 +1486,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       __syncthreads();
     }
     const uint32_t target = s_prefix;
-    int best = 0x7fffffff;
-    for (int j = threadIdx.x; j < n; j += kObjBlock)
-      if (speeds[j] == target) best = min(best, pixels[j]);
+    int best = obj_tie_break<kObjBlock>(speeds, pixels, n, !staged, target);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
     if (lane == 0 && best != 0x7fffffff) atomicMin(&s_best, best);
@@ -1496,28 +1585,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       const uint32_t prefix = *prefix0;
       const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
       const uint32_t binmask = (1u << bits) - 1u;
-      for (int j0 = 0; j0 < m; j0 += 4 * kObjBlock) {
-        uint32_t v[4];
-        bool ok[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int j = j0 + q * kObjBlock + threadIdx.x;
-          ok[q] = j < m;
-          v[q] = ok[q] ? speeds[j] : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          int bin = -1;
-          if (ok[q] && (v[q] & himask) == prefix) bin = static_cast<int>((v[q] >> shift) & binmask);
-          int uniform;
-          __match_all_sync(kFull, bin, &uniform);
-          if (uniform) {
-            if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
-          } else if (bin >= 0) {
-            atomicAdd(&hist[bin], 1u);
-          }
-        }
-      }
+      obj_hist_pass<kObjBlock>(hist, speeds, m, !staged, himask, prefix, shift, binmask);
       cluster.sync();  // every CTA's histogram is complete
       if (crank == 0) {
         // parallel suffix scan over the summed histograms: thread t owns bins hi = kBins-1-2t and hi-1
@@ -1563,9 +1631,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       cluster.sync();  // the new prefix is visible; rank 0 has finished reading the other histograms
     }
     const uint32_t target = *prefix0;
-    int best = 0x7fffffff;
-    for (int j = threadIdx.x; j < m; j += kObjBlock)
-      if (speeds[j] == target) best = min(best, pixels[j]);
+    int best = obj_tie_break<kObjBlock>(speeds, pixels, m, !staged, target);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(kFull, best, o));
     if (lane == 0 && best != 0x7fffffff) atomicMin(best0, best);
