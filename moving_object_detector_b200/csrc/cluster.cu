@@ -39,6 +39,9 @@
 #include <cooperative_groups.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace mod {
@@ -1710,15 +1713,35 @@ __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, si
   if (t < nc) c[t] = 0;
 }
 
+#include "cluster_scan.cuh"
+
+// Developer switch for same-run A/B measurements: MOD_B200_CL_TILE=scan selects the raster-scan kernel (cl_scan_kernel,
+// first version: 0.637 vs 0.559 ms of clusterer time on the benchmark) instead of the list-driven tile kernel.
+bool use_list_tile_kernel() {
+  static const bool lists = [] {
+    const char* e = getenv("MOD_B200_CL_TILE");
+    return e == nullptr || strcmp(e, "scan") != 0;
+  }();
+  return lists;
+}
+
 template <int NC>
 void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint32_t* border_list, uint32_t* root_list,
                        int* counters) {
   const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
-  if constexpr (NC > 0)
-    cl_tile_fast_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
-                                                     counters);
-  else
+  if constexpr (NC > 0) {
+    if (use_list_tile_kernel()) {
+      cl_tile_fast_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
+                                                       counters);
+    } else {
+      const int tiles_x = (L.w + (32 - NC) - 1) / (32 - NC);
+      const dim3 sgrid((tiles_x + CL_SCAN_WARPS - 1) / CL_SCAN_WARPS, (L.h + CL_SCAN_ROWS - 1) / CL_SCAN_ROWS, L.batch);
+      cl_scan_kernel<NC><<<sgrid, CL_SCAN_WARPS * 32, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask,
+                                                             root_list, counters);
+    }
+  } else {
     cl_tile_kernel<<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, root_list, counters);
+  }
   cl_merge_kernel<NC><<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
 }
 
