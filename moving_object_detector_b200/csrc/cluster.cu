@@ -1714,23 +1714,39 @@ __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, si
 }
 
 #include "cluster_scan.cuh"
+#include "cluster_wide.cuh"
 
 // Developer switch for same-run A/B measurements: MOD_B200_CL_TILE=scan selects the raster-scan kernel (cl_scan_kernel,
-// first version: 0.637 vs 0.559 ms of clusterer time on the benchmark) instead of the list-driven tile kernel.
-bool use_list_tile_kernel() {
-  static const bool lists = [] {
+// first version: 0.637 vs 0.559 ms of clusterer time on the benchmark), MOD_B200_CL_TILE=wide the halo-node kernel of
+// neighbor_distance 5..10 (cl_tile_wide_kernel) instead of the list-driven tile kernel for neighbor_distance 1..4.
+int tile_kernel_choice() {
+  static const int choice = [] {
     const char* e = getenv("MOD_B200_CL_TILE");
-    return e == nullptr || strcmp(e, "scan") != 0;
+    if (e != nullptr && strcmp(e, "scan") == 0) return 1;
+    if (e != nullptr && strcmp(e, "wide") == 0) return 2;
+    return 0;
   }();
-  return lists;
+  return choice;
 }
 
 template <int NC>
 void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint32_t* border_list, uint32_t* root_list,
                        int* counters) {
   const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
-  if constexpr (NC > 0) {
-    if (use_list_tile_kernel()) {
+  if constexpr (NC > 4) {
+    cl_tile_wide_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
+                                                     counters);
+    cl_merge_pairs_kernel<<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
+    return;
+  } else if constexpr (NC > 0) {
+    const int choice = tile_kernel_choice();
+    if (choice == 2) {
+      cl_tile_wide_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
+                                                       counters);
+      cl_merge_pairs_kernel<<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
+      return;
+    }
+    if (choice == 0) {
       cl_tile_fast_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
                                                        counters);
     } else {
@@ -1788,6 +1804,12 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
     case 2: launch_tile_merge<2>(s, L, X, border_list, root_list, counters); break;
     case 3: launch_tile_merge<3>(s, L, X, border_list, root_list, counters); break;
     case 4: launch_tile_merge<4>(s, L, X, border_list, root_list, counters); break;
+    case 5: launch_tile_merge<5>(s, L, X, border_list, root_list, counters); break;
+    case 6: launch_tile_merge<6>(s, L, X, border_list, root_list, counters); break;
+    case 7: launch_tile_merge<7>(s, L, X, border_list, root_list, counters); break;
+    case 8: launch_tile_merge<8>(s, L, X, border_list, root_list, counters); break;
+    case 9: launch_tile_merge<9>(s, L, X, border_list, root_list, counters); break;
+    case 10: launch_tile_merge<10>(s, L, X, border_list, root_list, counters); break;
     default: launch_tile_merge<0>(s, L, X, border_list, root_list, counters); break;
   }
   cl_roots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);

@@ -311,10 +311,11 @@ def test_clusters_image_matches_oracle(oracle):
             assert np.array_equal(img[i].cpu().numpy(), oracle.clusters_image(labels[i], int(st[i]["n_clusters"]), lut))
 
 
-@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("size", [(640, 400), (333, 217)])
 def test_every_neighbor_distance_path_matches_oracle(oracle, n, size):
-    """neighbor_distance 1..4 are separate instantiations of the fast tile kernel, 0 and >= 5 the generic kernel;
+    """neighbor_distance 1..4 are separate instantiations of the fast tile kernel, 5..10 of the halo-node kernel
+    (cl_tile_wide), 0 takes the generic kernel;
     both on a frame of whole tiles and on one with ragged right / bottom tiles and an odd width."""
     w, h = size
     cloud, _ = synth.make_stress_cloud(w, h, seed=100 + n, cluster_size=200)

@@ -100,7 +100,7 @@ def test_invalid_encodings_and_edge_flows(ctx, ref):
     assert_cloud_bit_exact(static, r["static_flow"])
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 10])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 10])
 def test_clusterer_stress_equals_the_reference_nodelet(ctx, ref, n):
     """Clusterer-stress structure (serpentine, blobs straddling cluster_size, specks, checkerboards, depth steps)
     at every kernel family (tile-fast N = 1..4, generic N = 5, 10)."""
