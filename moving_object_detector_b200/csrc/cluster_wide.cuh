@@ -12,14 +12,20 @@
 // local-memory arrays and handed those pixels to cl_merge, which re-evaluated their windows on global memory
 // (ncu, r02, 8 stress frames of 2208x1242 at N = 10: cl_tile 3.83 ms / 2.3 G warp instructions, cl_merge 0.80 ms).  Here:
 //
-//   * THE HALO PIXELS ARE NODES of the tile's union-find.  Labels live in the staged index space (32+N)^2, a core
-//     pixel's link may point into the halo, and every edge of a core pixel -- in-tile or cross-tile -- is settled in
-//     shared memory.  A component's representative towards the later kernels is its smallest CORE pixel (rep); every
+//   * THE HALO PIXELS ARE NODES of the tile's union-find.  Labels live in the staged index space (32+N)^2 and every
+//     edge of a core pixel -- in-tile or cross-tile -- is settled in shared memory.  A component's representative towards the later kernels is its smallest CORE pixel (rep); every
 //     halo pixel h that ended up in a component yields ONE pair (h, rep) for cl_merge_pairs, which unions the two tile
 //     roots in global memory (de-duplicated per warp).  No window is ever re-evaluated on global memory and no
 //     implied-edge elimination is needed: the number of global unions is bounded by the halo size, not by the edges.
 //     Every shared-memory union corresponds to an accepted edge of a core pixel, every accepted edge (a, b) is seen
 //     by the tile that holds a in its core, so the global partition equals the reference's.
+//   * HALO PIXELS START AS LEAVES.  Links (C1) only go to core cells -- z is staged twice, s_zc with +inf in the halo
+//     -- so the link forest's roots are core pixels; then every halo pixel looks for its nearest accepted core pixel
+//     (H) and takes that pixel's root as its label.  A halo pixel is nobody's parent at that point, so this needs no
+//     atomics, and on smooth depth the whole tile is one flat tree before the first compare.  (First version: links
+//     into the halo made the up to 740 halo pixels roots that had to be unioned with one another through core pixels,
+//     smallest index wins -- chains hundreds of links deep; ncu on the N = 10 stress frames: 38 % of the instructions
+//     in finds and unions.)  Edges from a core pixel to a halo pixel of another tree are found by C2 like any other.
 //   * LAZY DEPTH GATES.  C1 evaluates the window once, branch-free (one shared load, one subtract, one compare per
 //     cell; non-dynamic cells are staged as z = +inf) and keeps only the two raster-smallest accepted cells: the LINK
 //     (parent pointer to an earlier pixel: a forest, no atomics) and one more for the first merge round (C2a, one union
@@ -49,7 +55,8 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
                                        // pixel staged at p sits at p - kCore + wy * SW + wx
   constexpr int kHalo = NC * SW + kTileH * NC;
   constexpr int kNone = 0x7fffffff;
-  __shared__ float s_z[kCells];
+  __shared__ float s_z[kCells];        // z of every staged dynamic pixel, +inf elsewhere
+  __shared__ float s_zc[kCells];       // the same with +inf in the halo: what C1 links against
   __shared__ int s_lab[kCells];        // -1: not dynamic; otherwise a staged index of the same set
   __shared__ int s_rep[kCells];        // C1..C2a: second accepted cell of a core pixel; later: min core pixel per root
   __shared__ uint8_t s_up[kCells];     // core pixel has an accepted up-left neighbour
@@ -88,7 +95,9 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     const bool dyn = ((word >> (8 * j)) & 0xffu) != 0;
     const int si = (row + NC) * SW + NC + wq * 4 + j;
     s_lab[si] = dyn ? si : -1;
-    s_z[si] = dyn ? __ldg(pts + (static_cast<size_t>(y) * L.w + x0 + j) * 8 + 2) : CUDART_INF_F;
+    const float z = dyn ? __ldg(pts + (static_cast<size_t>(y) * L.w + x0 + j) * 8 + 2) : CUDART_INF_F;
+    s_z[si] = z;
+    s_zc[si] = z;
   }
   // halo: NC rows above (full width 32+NC) and NC columns to the left of the core
   constexpr int top = NC * SW;
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     const int si = sy * SW + sx;
     s_lab[si] = m ? si : -1;
     s_z[si] = m ? __ldg(pts + (static_cast<size_t>(yy) * L.w + xx) * 8 + 2) : CUDART_INF_F;
+    s_zc[si] = CUDART_INF_F;
   }
   __syncthreads();
 
@@ -129,22 +139,38 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
   auto gate_fast = [&](float z_here, int si) -> bool { return !(fabsf(__fsub_rn(z_here, s_z[si])) > thr); };
   auto gate_flag = [&](float z_here, int si) -> bool { return s_lab[si] >= 0 && depth_gate(z_here, s_z[si], thr); };
 
-  // C1: link to the raster-smallest accepted neighbour; remember the next one for C2a
+  // halo cell k (0 .. kHalo-1) -> staged index
+  auto halo_cell = [&](int k) -> int {
+    int sy, sx;
+    if (k < top) {
+      sy = k / SW;
+      sx = k - sy * SW;
+    } else {
+      const int k2 = k - top;
+      sy = NC + k2 / NC;
+      sx = k2 - (k2 / NC) * NC;
+    }
+    return sy * SW + sx;
+  };
+
+  // C1: link to the raster-smallest accepted CORE neighbour; remember the next one for C2a
   for (int e = threadIdx.x; e < nd; e += kBlock) {
     const int p = s_dl[e];
     const float z_here = s_z[p];
     const int base = p - kCore;
+    const int lx = p % SW - NC, ly = p / SW - NC;
     int first = -1, second = -1;
-    if (thr_ok && fabsf(z_here) < CUDART_INF_F) {
-      // a non-dynamic cell holds +inf: |finite - inf| = inf > thr rejects it.  Reverse raster order: the last hit is
-      // the raster-smallest one.
+    const bool fast = thr_ok && fabsf(z_here) < CUDART_INF_F;
+    if (fast) {
+      // a non-dynamic or halo cell holds +inf: |finite - inf| = inf > thr rejects it.  Reverse raster order: the last hit
+      // is the raster-smallest one.
 #pragma unroll
       for (int wy = NC; wy >= 0; wy--) {
 #pragma unroll
         for (int wx = NC; wx >= 0; wx--) {
           if (wy == NC && wx == NC) continue;
           const int si = base + wy * SW + wx;
-          if (gate_fast(z_here, si)) {
+          if (!(fabsf(__fsub_rn(z_here, s_zc[si])) > thr)) {
             second = first;
             first = si;
           }
@@ -153,14 +179,25 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     } else {  // z_here not finite (foreign clouds) or no usable threshold: test the dynamic flag explicitly
 #pragma unroll 1
       for (int k = S * S - 2; k >= 0; k--) {
-        const int si = base + (k / S) * SW + (k % S);
+        const int wy = k / S, wx = k % S;
+        if (lx - NC + wx < 0 || ly - NC + wy < 0) continue;  // halo cell
+        const int si = base + wy * SW + wx;
         if (gate_flag(z_here, si)) {
           second = first;
           first = si;
         }
       }
     }
-    s_up[p] = first >= 0;
+    bool up = first >= 0;
+    if (!up && (lx < NC || ly < NC)) {  // no accepted core cell: the key flag still needs the halo cells (rare)
+#pragma unroll 1
+      for (int k = 0; k < S * S - 1 && !up; k++) {
+        const int wy = k / S, wx = k % S;
+        if (lx - NC + wx >= 0 && ly - NC + wy >= 0) continue;  // core cell: seen above
+        up = gate_flag(z_here, base + wy * SW + wx);
+      }
+    }
+    s_up[p] = up;
     s_rep[p] = second;
     s_lab[p] = first >= 0 ? first : p;  // only p's own entry changes here and nobody reads a label's VALUE in C1
   }
@@ -169,6 +206,31 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
   for (int e = threadIdx.x; e < nd; e += kBlock) {  // F
     const int p = s_dl[e];
     s_lab[p] = smem_find_readonly(s_lab, p);
+  }
+  __syncthreads();
+  // H: every dynamic halo pixel takes the label (a root: the labels are flat) of its nearest accepted core pixel.  The
+  // halo pixel is still a singleton nobody points to, so a plain store does it.  A halo pixel that touches several
+  // trees joins one here; C2 finds the others.
+  for (int k = threadIdx.x; k < kHalo; k += kBlock) {
+    const int h = halo_cell(k);
+    if (s_lab[h] < 0) continue;
+    const float zh = s_z[h];
+    const int sy = h / SW, sx = h - sy * SW;
+    const int cy0 = max(sy, NC), cx0 = max(sx, NC);
+    const int cy1 = min(sy + NC, SH - 1), cx1 = min(sx + NC, SW - 1);
+    int found = -1;
+#pragma unroll 1
+    for (int cy = cy0; cy <= cy1 && found < 0; cy++) {
+#pragma unroll 1
+      for (int cx = cx0; cx <= cx1; cx++) {
+        const int c = cy * SW + cx;
+        if (s_lab[c] >= 0 && depth_gate(s_z[c], zh, thr)) {
+          found = c;
+          break;
+        }
+      }
+    }
+    if (found >= 0) s_lab[h] = s_lab[found];
   }
   __syncthreads();
   for (int e0 = 0; e0 < nd; e0 += kBlock) {  // C2a: one union per pixel, one lane per distinct (root, root) pair
@@ -194,6 +256,10 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
   for (int e = threadIdx.x; e < nd; e += kBlock) {  // F
     const int p = s_dl[e];
     s_lab[p] = smem_find_readonly(s_lab, p);
+  }
+  for (int k = threadIdx.x; k < kHalo; k += kBlock) {  // the halo leaves follow their trees
+    const int h = halo_cell(k);
+    if (s_lab[h] >= 0) s_lab[h] = smem_find_readonly(s_lab, h);
   }
   for (int k = threadIdx.x; k < kCells; k += kBlock) s_rep[k] = kNone;  // the second-cell slots are free now
   __syncthreads();
@@ -284,16 +350,7 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     bool joined = false;
     int si = 0;
     if (k < kHalo) {
-      int sy, sx;
-      if (k < top) {
-        sy = k / SW;
-        sx = k - sy * SW;
-      } else {
-        const int k2 = k - top;
-        sy = NC + k2 / NC;
-        sx = k2 - (k2 / NC) * NC;
-      }
-      si = sy * SW + sx;
+      si = halo_cell(k);
       // a halo pixel's set holds a core pixel iff some core pixel linked to it or was unioned with it
       if (s_lab[si] >= 0) joined = s_rep[smem_find_readonly(s_lab, si)] != kNone;
     }
