@@ -266,6 +266,25 @@ int mod_image_crop_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int bat
 int mod_host_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
                               double* out_K9, double* out_P12);
 
+/* ---- MONO8 conversion (upstream glue) ------------------------------------------------------ */
+/* SceneFlowConstructor::estimateCameraMotion (scene_flow_constructor/src/scene_flow_constructor.cpp:220-221):
+ * cv_bridge::toCvCopy(image, MONO8) of the left and right camera image in front of the viso2 odometer, i.e.
+ * cv::cvtColor(COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit pixels (a mono8 source is copied):
+ *     grey = (cB*B + cG*G + cR*R + (1 << (shift-1))) >> shift.
+ * The constants belong to the OpenCV the node is linked against, so the caller names them:
+ *   MOD_GRAY_OPENCV3  (cR, cG, cB, shift) = (4899, 9617, 1868, 14)  -- OpenCV 2.4 / 3.x, the reference's ROS Melodic build
+ *   MOD_GRAY_OPENCV4  (cR, cG, cB, shift) = (9798, 19235, 3735, 15) -- OpenCV 4.x
+ * Output: dense mono8, h rows of w bytes (what viso2's process() receives as dims = {w, h, w}). */
+enum { MOD_GRAY_OPENCV3 = 0, MOD_GRAY_OPENCV4 = 1 };
+/* Host seam: data = sensor_msgs/Image.data (h rows of step_bytes) in `encoding` (MOD_ENC_*). */
+int mod_image_to_mono8(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int rule,
+                       uint8_t* out_mono8);
+/* Device-resident batch: frame i starts at d_data + i*frame_stride_bytes; d_out_mono8 = batch dense images.
+ * Asynchronous on `stream`. */
+int mod_image_to_mono8_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, int encoding,
+                                   const uint8_t* d_data, size_t frame_stride_bytes, int32_t step_bytes, int rule,
+                                   uint8_t* d_out_mono8);
+
 /* ---- static-flow filter (diagnostics) ------------------------------------------------------------------------ */
 /* The scene-flow kernel decides the residual gate (scene_flow_constructor.cpp:191-198) from a float evaluation of
  * the static flow with a rigorous error bound and re-evaluates undecided pixels with the reference's exact

@@ -129,6 +129,9 @@ PROTOTYPES = {
                                  C.c_void_p]),
     "mod_image_crop_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              C.c_size_t, C.c_int32, C.c_int, C.c_int, C.c_void_p]),
+    "mod_image_to_mono8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
+    "mod_image_to_mono8_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                 C.c_size_t, C.c_int32, C.c_int, C.c_void_p]),
     "mod_host_crop_camera_info": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]),
     "mod_pipeline_sequence_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Camera), C.c_float,

@@ -307,6 +307,28 @@ class Context:
                                                          _dev_ptr(data), frame_stride_bytes, step_bytes, target_w,
                                                          target_h, _dev_ptr(out_bgr8)))
 
+    # ---- MONO8 conversion (upstream glue) -----------------------------------------------------------------------
+    def to_mono8(self, image: np.ndarray, encoding: str, rule: int = 0) -> np.ndarray:
+        """cv_bridge::toCvCopy(image, MONO8) of estimateCameraMotion (scene_flow_constructor.cpp:220-221): (H,W[,C])
+        uint8 in `encoding` (rows may be strided) -> (H,W) uint8.  rule: 0 = OpenCV 3.x grey constants (the
+        reference's build), 1 = OpenCV 4.x."""
+        assert image.dtype == np.uint8 and image.strides[-1] == 1
+        h, w = image.shape[:2]
+        row_bytes = image[0].size if h else 0
+        step = image.strides[0] if h > 1 else row_bytes
+        buf = np.zeros((h, step), np.uint8)
+        buf[:, :row_bytes] = image.reshape(h, row_bytes)
+        out = np.empty((h, w), np.uint8)
+        self._check(self._lib.mod_image_to_mono8(self._h, w, h, ENCODINGS[encoding], buf.ctypes.data, step, int(rule),
+                                                 out.ctypes.data))
+        return out
+
+    def to_mono8_batched_dev(self, w: int, h: int, batch: int, encoding: str, data, frame_stride_bytes: int,
+                             step_bytes: int, rule: int, out_mono8, stream: int = 0):
+        self._check(self._lib.mod_image_to_mono8_batched_dev(self._h, stream or None, w, h, batch, ENCODINGS[encoding],
+                                                             _dev_ptr(data), frame_stride_bytes, step_bytes, int(rule),
+                                                             _dev_ptr(out_mono8)))
+
     # ---- fused ----------------------------------------------------------------------------------------------
     def pipeline(self, now: DisparityImage, prev: DisparityImage, flow: np.ndarray, cam: CameraInfo,
                  prev2now: TransformMsg, dt_sec: float, sf_config: SceneFlowConstructorConfig = None,

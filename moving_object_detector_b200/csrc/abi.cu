@@ -973,6 +973,46 @@ int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data
   return MOD_OK;
 }
 
+int mod_image_to_mono8_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, int encoding,
+                                   const uint8_t* d_data, size_t frame_stride_bytes, int32_t step_bytes, int rule,
+                                   uint8_t* d_out_mono8) {
+  if (!ctx) return MOD_ERR_INVALID_ARG;
+  if (w <= 0 || h <= 0 || batch <= 0) return fail(ctx, MOD_ERR_INVALID_ARG, "bad image size or batch");
+  if (encoding < MOD_ENC_BGR8 || encoding > MOD_ENC_MONO8) return fail(ctx, MOD_ERR_INVALID_ARG, "unknown encoding %d", encoding);
+  if (rule != MOD_GRAY_OPENCV3 && rule != MOD_GRAY_OPENCV4) return fail(ctx, MOD_ERR_INVALID_ARG, "unknown grey rule %d", rule);
+  static const int bpp_of[5] = {3, 3, 4, 4, 1};
+  if (step_bytes < w * bpp_of[encoding]) return fail(ctx, MOD_ERR_INVALID_ARG, "step %d shorter than a row", step_bytes);
+  if (!d_data || !d_out_mono8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  MOD_CK(ctx, launch_to_mono8(static_cast<cudaStream_t>(stream), d_data, frame_stride_bytes, step_bytes, encoding, w, h,
+                              batch, rule, d_out_mono8));
+  ctx->launches++;
+  return MOD_OK;
+}
+
+int mod_image_to_mono8(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int rule,
+                       uint8_t* out_mono8) {
+  int rc = check_size(ctx, w, h, 1);
+  if (rc != MOD_OK) return rc;
+  if (!data || !out_mono8) return fail(ctx, MOD_ERR_INVALID_ARG, "null argument");
+  if (step_bytes <= 0 || static_cast<size_t>(step_bytes) > 16 * static_cast<size_t>(ctx->max_w))
+    return fail(ctx, MOD_ERR_INVALID_ARG, "step %d outside (0, 16*max_w]", step_bytes);
+  MOD_CK(ctx, cudaSetDevice(ctx->device));
+  rc = ensure_host_staging(ctx);
+  if (rc != MOD_OK) return rc;
+  // staging as in mod_image_crop: source in the first half of the cloud buffer, result in the second half
+  cudaStream_t s = ctx->stream;
+  ctx->cloud_w = ctx->cloud_h = 0;
+  uint8_t* d_src = reinterpret_cast<uint8_t*>(ctx->d_points);
+  uint8_t* d_out = d_src + 16 * static_cast<size_t>(ctx->max_w) * ctx->max_h;
+  MOD_CK(ctx, ctx->stager.h2d(d_src, data, static_cast<size_t>(step_bytes) * h, s));
+  rc = mod_image_to_mono8_batched_dev(ctx, s, w, h, 1, encoding, d_src, 0, step_bytes, rule, d_out);
+  if (rc != MOD_OK) return rc;
+  MOD_CK(ctx, ctx->stager.d2h(out_mono8, d_out, static_cast<size_t>(w) * h, s));
+  MOD_CK(ctx, cudaStreamSynchronize(s));
+  return MOD_OK;
+}
+
 int mod_host_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
                               double* out_K9, double* out_P12) {
   int x0, y0;

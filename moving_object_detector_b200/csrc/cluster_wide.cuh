@@ -190,11 +190,12 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     }
     bool up = first >= 0;
     if (!up && (lx < NC || ly < NC)) {  // no accepted core cell: the key flag still needs the halo cells (rare)
+      const int hy = max(NC - ly, 0), hx = max(NC - lx, 0);  // window rows < hy are halo rows, columns < hx halo columns
 #pragma unroll 1
-      for (int k = 0; k < S * S - 1 && !up; k++) {
-        const int wy = k / S, wx = k % S;
-        if (lx - NC + wx >= 0 && ly - NC + wy >= 0) continue;  // core cell: seen above
-        up = gate_flag(z_here, base + wy * SW + wx);
+      for (int wy = 0; wy < S && !up; wy++) {
+        const int n = wy < hy ? S : hx;  // hx <= NC: the pixel's own cell (NC, NC) is never reached
+#pragma unroll 1
+        for (int wx = 0; wx < n; wx++) up = up || gate_flag(z_here, base + wy * SW + wx);
       }
     }
     s_up[p] = up;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
   bool unioned = false;
   for (int e0 = 0; e0 < nd; e0 += kBlock) {
     const int e = e0 + threadIdx.x;
-    int p = kCore, my = -2;
+    int p = kCore, my = 0;
     float z_here = 0.0f;
     bool fast = true;
     if (e < nd) {
@@ -284,8 +285,9 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
       uint32_t m = 0u;
 #pragma unroll
       for (int wx = 0; wx <= NC; wx++) {
-        const int l = s_lab[rb + wx];
-        if (l != my && l >= 0) m |= 1u << wx;
+        // foreign label: l >= 0 and l != my.  my >= 0, so (l ^ my) is 0 for an equal label, negative for l = -1 (not
+        // dynamic) and positive exactly for a foreign one
+        if ((s_lab[rb + wx] ^ my) > 0) m |= 1u << wx;
       }
       if (wy == NC) m &= ~(1u << NC);  // the pixel itself
       if (e >= nd) m = 0u;

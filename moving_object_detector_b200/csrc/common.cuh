@@ -138,6 +138,9 @@ cudaError_t launch_clusters_image(cudaStream_t s, const int32_t* labels, const m
 // glue.cu: image_crop (image_crop/src/image_crop.cpp:20-43).  encoding: MOD_ENC_* of include/mod_b200.h
 cudaError_t launch_image_crop(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding,
                               int x0, int y0, int tw, int th, int batch, uint8_t* out);
+// glue.cu: cv_bridge::toCvCopy(image, MONO8) (scene_flow_constructor.cpp:220-221).  rule: MOD_GRAY_* of include/mod_b200.h
+cudaError_t launch_to_mono8(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding, int w,
+                            int h, int batch, int rule, uint8_t* out);
 void host_hsv_colormap(uint8_t* bgr768);
 
 // float threshold equivalents of the reference's float-vs-double comparisons

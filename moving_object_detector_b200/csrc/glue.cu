@@ -1,4 +1,4 @@
-// glue.cu -- upstream glue of the hot path on the GPU: image_crop.
+// glue.cu -- upstream glue of the hot path on the GPU: image_crop, MONO8 conversion.
 //
 //   image_crop::ImageCrop::cameraCallback      image_crop/src/image_crop.cpp:20-43
 // crops the camera image to target_width x target_height around the image centre after cv_bridge::toCvShare(msg,
@@ -7,6 +7,15 @@
 // stores) of the dense bgr8 result; reads of neighbouring threads are contiguous, so both sides move whole sectors.
 // Two kernels: word loads + funnel shift + byte permute when a thread's four pixels share a row (target_w % 4 == 0),
 // a byte-wise kernel otherwise.  Pure byte moves: HBM-bound, bit-exact by construction.
+//
+//   cv_bridge::toCvCopy(image, MONO8)           scene_flow_constructor/src/scene_flow_constructor.cpp:220-221
+// converts both camera images to 8-bit grey in front of the viso2 odometer: cv::cvtColor with COLOR_BGR2GRAY /
+// RGB2GRAY / BGRA2GRAY / RGBA2GRAY, which for 8-bit images is fixed-point arithmetic,
+//     grey = (cB * B + cG * G + cR * R + (1 << (shift - 1))) >> shift,
+// with (cR, cG, cB, shift) = (4899, 9617, 1868, 14) in the OpenCV 3.2 the reference is built against (ROS Melodic;
+// imgproc/src/color.cpp: R2Y, G2Y, B2Y, yuv_shift) and (9798, 19235, 3735, 15) from OpenCV 4 on (RY15, GY15, BY15,
+// gray_shift).  Both rules are integer-exact; the caller names the one its OpenCV uses (MOD_GRAY_*).  A mono8 source
+// is copied.  One pass, four output pixels (one aligned 32-bit store) per thread on the fast path.
 #include "common.cuh"
 
 namespace mod {
@@ -110,7 +119,125 @@ __global__ void __launch_bounds__(256) image_crop_rows_kernel(const CropParams p
   }
 }
 
+struct GrayParams {
+  const uint8_t* src;
+  uint8_t* out;
+  size_t src_frame_stride;  // bytes between consecutive source frames
+  int step;                 // source row stride in bytes
+  int w, h, batch;
+  int bpp;                  // source bytes per pixel (1: copy)
+  int c0, c1, c2, shift;    // weights of source bytes 0, 1, 2 of a pixel
+};
+
+__device__ __forceinline__ uint32_t grey_of(uint32_t b0, uint32_t b1, uint32_t b2, const GrayParams& p) {
+  return (b0 * p.c0 + b1 * p.c1 + b2 * p.c2 + (1u << (p.shift - 1))) >> p.shift;
+}
+
+// general path: one output pixel per thread, byte loads
+__global__ void __launch_bounds__(256) to_mono8_kernel(const GrayParams p) {
+  const size_t per_frame = static_cast<size_t>(p.w) * p.h;
+  const size_t total = per_frame * p.batch;
+  for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t frame = g / per_frame;
+    const size_t in_frame = g - frame * per_frame;
+    const int r = static_cast<int>(in_frame / p.w);
+    const int c = static_cast<int>(in_frame - static_cast<size_t>(r) * p.w);
+    const uint8_t* s = p.src + frame * p.src_frame_stride + static_cast<size_t>(r) * p.step + static_cast<size_t>(c) * p.bpp;
+    p.out[g] = p.bpp == 1 ? __ldg(s) : static_cast<uint8_t>(grey_of(__ldg(s), __ldg(s + 1), __ldg(s + 2), p));
+  }
+}
+
+// fast path (w % 4 == 0, 4-byte aligned output): a thread's four pixels are one contiguous run of 4 * kBpp source
+// bytes, fetched as aligned 32-bit words and funnel-shifted into place (as in image_crop_rows_kernel)
+template <int kBpp>
+__global__ void __launch_bounds__(256) to_mono8_rows_kernel(const GrayParams p) {
+  constexpr int kU = 4;  // groups per thread and pass, a grid stride apart: their loads are all issued before the first
+                         // use (12 .. 16 bytes per group would leave too few bytes in flight per SM to fill HBM)
+  const int groups_per_row = p.w >> 2;
+  const size_t groups = static_cast<size_t>(groups_per_row) * p.h * p.batch;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t g0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g0 < groups; g0 += stride * kU) {
+    uint32_t wsrc[kU][kBpp + 1];
+    unsigned shift[kU];
+    size_t opos[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const size_t g = g0 + u * stride;
+      shift[u] = 0;
+      opos[u] = 0;
+#pragma unroll
+      for (int k = 0; k <= kBpp; k++) wsrc[u][k] = 0u;
+      if (g < groups) {
+        const size_t row = g / groups_per_row;  // frame * h + r
+        const int c = static_cast<int>(g - row * groups_per_row) << 2;
+        const size_t frame = row / p.h;
+        const int r = static_cast<int>(row - frame * p.h);
+        const uint8_t* s = p.src + frame * p.src_frame_stride + static_cast<size_t>(r) * p.step + static_cast<size_t>(c) * kBpp;
+        shift[u] = static_cast<unsigned>(reinterpret_cast<uintptr_t>(s) & 3u);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s - shift[u]);
+#pragma unroll
+        for (int k = 0; k < kBpp; k++) wsrc[u][k] = __ldg(wp + k);
+        if (shift[u]) wsrc[u][kBpp] = __ldg(wp + kBpp);  // only touched when the run really extends into it
+        opos[u] = row * p.w + c;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      if (g0 + u * stride >= groups) break;
+      uint32_t a[kBpp];
+#pragma unroll
+      for (int k = 0; k < kBpp; k++) a[k] = __funnelshift_r(wsrc[u][k], wsrc[u][k + 1], 8 * shift[u]);
+      uint32_t o = 0;
+      if constexpr (kBpp == 1) {
+        o = a[0];
+      } else {
+#pragma unroll
+        for (int px = 0; px < 4; px++) {
+          uint32_t b[3];
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const int sb = px * kBpp + ch;
+            b[ch] = (a[sb >> 2] >> (8 * (sb & 3))) & 0xffu;
+          }
+          o |= grey_of(b[0], b[1], b[2], p) << (8 * px);
+        }
+      }
+      *reinterpret_cast<uint32_t*>(p.out + opos[u]) = o;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_to_mono8(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding, int w,
+                            int h, int batch, int rule, uint8_t* out) {
+  static const int bpp_of[5] = {3, 3, 4, 4, 1};
+  // (cR, cG, cB, shift): OpenCV 3.x (R2Y, G2Y, B2Y, yuv_shift) / OpenCV 4.x (RY15, GY15, BY15, gray_shift)
+  static const int rules[2][4] = {{4899, 9617, 1868, 14}, {9798, 19235, 3735, 15}};
+  const size_t total = static_cast<size_t>(w) * h * batch;
+  if (total == 0) return cudaSuccess;
+  const bool blue_first = encoding == MOD_ENC_BGR8 || encoding == MOD_ENC_BGRA8;
+  const int* k = rules[rule];
+  GrayParams p{src, out, src_frame_stride, step, w, h, batch, bpp_of[encoding], blue_first ? k[2] : k[0], k[1],
+               blue_first ? k[0] : k[2], k[3]};
+  if (w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    size_t blocks = (total / 16 + 255) / 256;  // four groups of four pixels per thread and pass
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks == 0) blocks = 1;
+    const unsigned nb = static_cast<unsigned>(blocks);
+    switch (p.bpp) {
+      case 3: to_mono8_rows_kernel<3><<<nb, 256, 0, s>>>(p); break;
+      case 4: to_mono8_rows_kernel<4><<<nb, 256, 0, s>>>(p); break;
+      default: to_mono8_rows_kernel<1><<<nb, 256, 0, s>>>(p); break;
+    }
+    return cudaGetLastError();
+  }
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  to_mono8_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_image_crop(cudaStream_t s, const uint8_t* src, size_t src_frame_stride, int step, int encoding,
                               int x0, int y0, int tw, int th, int batch, uint8_t* out) {

@@ -752,6 +752,32 @@ int orc_image_crop(int w, int h, int encoding, const uint8_t* data, int32_t step
   return 0;
 }
 
+// cv_bridge::toCvCopy(image, MONO8) (scene_flow_constructor.cpp:220-221) = cv::cvtColor(..., COLOR_*2GRAY) on 8-bit
+// pixels: OpenCV's RGB2Gray<uchar> (imgproc/src/color.cpp; color_rgb.simd.hpp from 4.x on) is the fixed-point sum
+// (cb*B + cg*G + cr*R + (1 << (shift-1))) >> shift.  rule 0: OpenCV 2.4 / 3.x (R2Y 4899, G2Y 9617, B2Y 1868, yuv_shift
+// 14) -- the reference's OpenCV 3.2; rule 1: OpenCV 4.x (RY15 9798, GY15 19235, BY15 3735, gray_shift 15), which is the
+// cv2 of this image and what tests/test_mono8.py pins the arithmetic against.  A mono8 source is copied.
+int orc_to_mono8(int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int rule, uint8_t* out) {
+  static const int bpp_of[5] = {3, 3, 4, 4, 1};
+  static const int rules[2][4] = {{4899, 9617, 1868, 14}, {9798, 19235, 3735, 15}};  // cR, cG, cB, shift
+  if (encoding < 0 || encoding > 4 || rule < 0 || rule > 1 || !data || !out) return -1;
+  const int bpp = bpp_of[encoding];
+  const bool blue_first = encoding == 0 || encoding == 2;
+  const int cr = rules[rule][0], cg = rules[rule][1], cb = rules[rule][2], shift = rules[rule][3];
+  for (int r = 0; r < h; r++)
+    for (int c = 0; c < w; c++) {
+      const uint8_t* p = data + static_cast<size_t>(r) * step_bytes + static_cast<size_t>(c) * bpp;
+      uint8_t* q = out + static_cast<size_t>(r) * w + c;
+      if (bpp == 1) {
+        *q = p[0];
+      } else {
+        const int B = blue_first ? p[0] : p[2], G = p[1], R = blue_first ? p[2] : p[0];
+        *q = static_cast<uint8_t>((cb * B + cg * G + cr * R + (1 << (shift - 1))) >> shift);
+      }
+    }
+  return 0;
+}
+
 void orc_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h, const double* K9, const double* P12,
                           double* out_K9, double* out_P12) {
   uint32_t ox, oy;

@@ -154,6 +154,21 @@ def image_crop(image, encoding, target_w, target_h):
     return out
 
 
+def to_mono8(image, encoding, rule=0):
+    """cv_bridge::toCvCopy(image, MONO8): (H,W[,C]) uint8 in `encoding` -> (H,W) uint8.  rule 0 = OpenCV 3.x constants
+    (the reference's), 1 = OpenCV 4.x."""
+    lib = load()
+    assert image.dtype == np.uint8 and image.strides[-1] == 1
+    h, w = image.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    lib.orc_to_mono8.restype = C.c_int
+    rc = lib.orc_to_mono8(w, h, ENCODINGS[encoding], C.c_void_p(image.ctypes.data),
+                          C.c_int32(image.strides[0] if h > 1 else image[0].size), C.c_int(rule),
+                          C.c_void_p(out.ctypes.data))
+    assert rc == 0, rc
+    return out
+
+
 def crop_camera_info(w, h, target_w, target_h, K, P):
     lib = load()
     K = np.ascontiguousarray(K, np.float64).ravel()

@@ -23,7 +23,7 @@ def main(path, *filters):
     for name, ops in kernels.items():
         if filters and not any(f in name for f in filters):
             continue
-        short = re.sub(r"\(.*", "", name).replace("mod::(anonymous namespace)::", "")
+        short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "")).replace("void ", "").replace("mod::", "")
         total = sum(ops.values())
         base = collections.Counter()
         for op, n in ops.items():
