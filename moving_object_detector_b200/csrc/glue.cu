@@ -152,39 +152,42 @@ __global__ void __launch_bounds__(256) to_mono8_kernel(const GrayParams p) {
 // bytes, fetched as aligned 32-bit words and funnel-shifted into place (as in image_crop_rows_kernel)
 template <int kBpp>
 __global__ void __launch_bounds__(256) to_mono8_rows_kernel(const GrayParams p) {
-  constexpr int kU = 4;  // groups per thread and pass, a grid stride apart: their loads are all issued before the first
-                         // use (12 .. 16 bytes per group would leave too few bytes in flight per SM to fill HBM)
+  // A CTA owns kU consecutive image rows (of the batch's frames laid end to end); a thread takes the same group of four
+  // columns in each of them, so kU independent runs are loaded before the first one is used (12 .. 16 bytes per thread
+  // leave too few bytes in flight per SM to fill HBM) and the only division is one per CTA.
+  constexpr int kU = 4;
   const int groups_per_row = p.w >> 2;
-  const size_t groups = static_cast<size_t>(groups_per_row) * p.h * p.batch;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t g0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g0 < groups; g0 += stride * kU) {
+  const unsigned rows_total = static_cast<unsigned>(p.h) * p.batch;
+  const unsigned row0 = blockIdx.x * kU;
+  unsigned frame0 = row0 / p.h;
+  const int r0 = static_cast<int>(row0 - frame0 * p.h);
+  for (int cg = threadIdx.x; cg < groups_per_row; cg += blockDim.x) {
+    const int c = cg << 2;
     uint32_t wsrc[kU][kBpp + 1];
     unsigned shift[kU];
-    size_t opos[kU];
 #pragma unroll
     for (int u = 0; u < kU; u++) {
-      const size_t g = g0 + u * stride;
       shift[u] = 0;
-      opos[u] = 0;
 #pragma unroll
       for (int k = 0; k <= kBpp; k++) wsrc[u][k] = 0u;
-      if (g < groups) {
-        const size_t row = g / groups_per_row;  // frame * h + r
-        const int c = static_cast<int>(g - row * groups_per_row) << 2;
-        const size_t frame = row / p.h;
-        const int r = static_cast<int>(row - frame * p.h);
+      if (row0 + u < rows_total) {
+        int r = r0 + u;
+        unsigned frame = frame0;
+        if (r >= p.h) {  // kU <= h is not required: wrap as often as needed
+          frame += r / p.h;
+          r = r % p.h;
+        }
         const uint8_t* s = p.src + frame * p.src_frame_stride + static_cast<size_t>(r) * p.step + static_cast<size_t>(c) * kBpp;
         shift[u] = static_cast<unsigned>(reinterpret_cast<uintptr_t>(s) & 3u);
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(s - shift[u]);
 #pragma unroll
         for (int k = 0; k < kBpp; k++) wsrc[u][k] = __ldg(wp + k);
         if (shift[u]) wsrc[u][kBpp] = __ldg(wp + kBpp);  // only touched when the run really extends into it
-        opos[u] = row * p.w + c;
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; u++) {
-      if (g0 + u * stride >= groups) break;
+      if (row0 + u >= rows_total) break;
       uint32_t a[kBpp];
 #pragma unroll
       for (int k = 0; k < kBpp; k++) a[k] = __funnelshift_r(wsrc[u][k], wsrc[u][k + 1], 8 * shift[u]);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(256) to_mono8_rows_kernel(const GrayParams p) 
           o |= grey_of(b[0], b[1], b[2], p) << (8 * px);
         }
       }
-      *reinterpret_cast<uint32_t*>(p.out + opos[u]) = o;
+      *reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(row0 + u) * p.w + c) = o;
     }
   }
 }
@@ -222,10 +225,9 @@ cudaError_t launch_to_mono8(cudaStream_t s, const uint8_t* src, size_t src_frame
   GrayParams p{src, out, src_frame_stride, step, w, h, batch, bpp_of[encoding], blue_first ? k[2] : k[0], k[1],
                blue_first ? k[0] : k[2], k[3]};
   if (w % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
-    size_t blocks = (total / 16 + 255) / 256;  // four groups of four pixels per thread and pass
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks == 0) blocks = 1;
-    const unsigned nb = static_cast<unsigned>(blocks);
+    const size_t rows = static_cast<size_t>(h) * batch;
+    if (rows > 0xffffffffull) return cudaErrorInvalidValue;
+    const unsigned nb = static_cast<unsigned>((rows + 3) / 4);  // four rows per CTA
     switch (p.bpp) {
       case 3: to_mono8_rows_kernel<3><<<nb, 256, 0, s>>>(p); break;
       case 4: to_mono8_rows_kernel<4><<<nb, 256, 0, s>>>(p); break;

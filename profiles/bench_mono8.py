@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""MONO8 conversion (mod_image_to_mono8_batched_dev) on one B200: 128 cropped 1024x576 frames per launch (both cameras
-of 64 stereo pairs), device-resident, CUDA events.  Algorithmic bytes = pixels x (source bytes per pixel + 1).
+"""MONO8 conversion (mod_image_to_mono8_batched_dev) on one B200: 512 cropped 1024x576 frames per launch (both cameras
+of 256 stereo pairs; smaller batches time the host-side launch path instead of the kernel), device-resident, CUDA events.  Algorithmic bytes = pixels x (source bytes per pixel + 1).
     python profiles/bench_mono8.py > profiles/r02_mono8.jsonl"""
 import json
 import os
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from moving_object_detector_b200 import Context  # noqa: E402
 
-W, H, BATCH = 1024, 576, 128
+W, H, BATCH = 1024, 576, 512
 peak = 6544.0
 try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
