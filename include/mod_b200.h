@@ -276,6 +276,9 @@ int mod_host_crop_camera_info(uint32_t w, uint32_t h, int target_w, int target_h
  *   MOD_GRAY_OPENCV4  (cR, cG, cB, shift) = (9798, 19235, 3735, 15) -- OpenCV 4.x
  * Output: dense mono8, h rows of w bytes (what viso2's process() receives as dims = {w, h, w}). */
 enum { MOD_GRAY_OPENCV3 = 0, MOD_GRAY_OPENCV4 = 1 };
+/* sensor_msgs/Image.encoding -> MOD_ENC_* ("bgr8", "rgb8", "bgra8", "rgba8", "mono8"); MOD_ERR_INVALID_ARG for the
+ * encodings neither image_crop nor the MONO8 conversion take.  Host only. */
+int mod_host_encoding(const char* ros_encoding);
 /* Host seam: data = sensor_msgs/Image.data (h rows of step_bytes) in `encoding` (MOD_ENC_*). */
 int mod_image_to_mono8(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data, int32_t step_bytes, int rule,
                        uint8_t* out_mono8);

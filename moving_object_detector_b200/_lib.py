@@ -129,6 +129,7 @@ PROTOTYPES = {
                                  C.c_void_p]),
     "mod_image_crop_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              C.c_size_t, C.c_int32, C.c_int, C.c_int, C.c_void_p]),
+    "mod_host_encoding": (C.c_int, [C.c_char_p]),
     "mod_image_to_mono8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int32, C.c_int, C.c_void_p]),
     "mod_image_to_mono8_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                  C.c_size_t, C.c_int32, C.c_int, C.c_void_p]),

@@ -973,6 +973,14 @@ int mod_image_crop(mod_ctx* ctx, int w, int h, int encoding, const uint8_t* data
   return MOD_OK;
 }
 
+int mod_host_encoding(const char* ros_encoding) {
+  static const char* const names[5] = {"bgr8", "rgb8", "bgra8", "rgba8", "mono8"};
+  if (!ros_encoding) return MOD_ERR_INVALID_ARG;
+  for (int i = 0; i < 5; i++)
+    if (strcmp(ros_encoding, names[i]) == 0) return i;
+  return MOD_ERR_INVALID_ARG;
+}
+
 int mod_image_to_mono8_batched_dev(mod_ctx* ctx, void* stream, int w, int h, int batch, int encoding,
                                    const uint8_t* d_data, size_t frame_stride_bytes, int32_t step_bytes, int rule,
                                    uint8_t* d_out_mono8) {

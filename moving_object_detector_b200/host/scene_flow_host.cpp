@@ -131,6 +131,28 @@ void describeVelocityCloud(sensor_msgs::PointCloud2& msg, uint32_t width, uint32
   msg.is_dense = true;  // pcl::PointCloud(w, h, value) leaves is_dense = true although the cloud holds NaN
 }
 
+bool SceneFlowConstructorB200::toMono8(const sensor_msgs::Image& image, std::vector<uint8_t>& mono8, int rule) {
+  last_error_.clear();
+  const int encoding = mod_host_encoding(image.encoding.c_str());
+  if (encoding < 0) {
+    last_error_ = "toMono8: unsupported encoding " + image.encoding;
+    return false;
+  }
+  if (image.data.size() < static_cast<size_t>(image.step) * image.height) {
+    last_error_ = "toMono8: image data shorter than step * height";
+    return false;
+  }
+  mono8.resize(static_cast<size_t>(image.width) * image.height);
+  if (mono8.empty()) return true;
+  const int rc = mod_image_to_mono8(ctx_, static_cast<int>(image.width), static_cast<int>(image.height), encoding,
+                                    image.data.data(), static_cast<int32_t>(image.step), rule, mono8.data());
+  if (rc != MOD_OK) {
+    last_error_ = std::string("toMono8: ") + mod_last_error(ctx_);
+    return false;
+  }
+  return true;
+}
+
 bool SceneFlowConstructorB200::construct(const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_now,
                                          const std::shared_ptr<const stereo_msgs::DisparityImage>& disparity_previous,
                                          const std::shared_ptr<const sensor_msgs::Image>& left_flow,
@@ -425,10 +447,7 @@ ImageCropB200::~ImageCropB200() { mod_destroy(ctx_); }
 bool ImageCropB200::cameraCallback(const sensor_msgs::Image& image_msg, const sensor_msgs::CameraInfo& camera_info) {
   last_error_.clear();
   // cv_bridge::toCvShare(image_msg, "bgr8") (:23): the 8-bit colour encodings convert by channel shuffles
-  static const char* const names[5] = {"bgr8", "rgb8", "bgra8", "rgba8", "mono8"};
-  int encoding = -1;
-  for (int i = 0; i < 5; i++)
-    if (image_msg.encoding == names[i]) encoding = i;
+  const int encoding = mod_host_encoding(image_msg.encoding.c_str());
   if (encoding < 0) {
     last_error_ = "image_crop: unsupported encoding " + image_msg.encoding;
     return false;

@@ -87,6 +87,11 @@ class SceneFlowConstructorB200 {
   double clusterer_depth_diff = 0.15, clusterer_dynamic_speed = 0.3;
   int clusterer_neighbor_distance = 4;
 
+  // cv_bridge::toCvCopy(image, MONO8) of estimateCameraMotion (:220-221): dense width x height bytes for viso2's
+  // process().  rule = MOD_GRAY_OPENCV3 (the reference's OpenCV 3.2 constants) or MOD_GRAY_OPENCV4.  false + lastError()
+  // for an encoding cv_bridge would have to convert differently (16-bit, Bayer, ...).
+  bool toMono8(const sensor_msgs::Image& image, std::vector<uint8_t>& mono8, int rule = MOD_GRAY_OPENCV3);
+
   const std::string& lastError() const { return last_error_; }
   mod_ctx* context() const { return ctx_; }
 
