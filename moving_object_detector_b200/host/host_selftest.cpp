@@ -227,6 +227,24 @@ int main(int argc, char** argv) {
       image_crop::ImageCropB200 too_big(static_cast<int>(w), static_cast<int>(h), static_cast<int>(w + 1), static_cast<int>(h));
       too_big.camera_pub_ = crop.camera_pub_;
       if (too_big.cameraCallback(src, ci) || n_pub != 1) return fail("a window larger than the image was published");
+
+      // estimateCameraMotion's MONO8 conversion of the same (strided, rgba8) camera image, both grey rules
+      std::vector<uint8_t> mono;
+      for (int rule = MOD_GRAY_OPENCV3; rule <= MOD_GRAY_OPENCV4; rule++) {
+        if (!constructor.toMono8(src, mono, rule) || mono.size() != static_cast<size_t>(w) * h)
+          return fail(constructor.lastError().c_str());
+        const int cr = rule == MOD_GRAY_OPENCV3 ? 4899 : 9798, cg = rule == MOD_GRAY_OPENCV3 ? 9617 : 19235,
+                  cb = rule == MOD_GRAY_OPENCV3 ? 1868 : 3735, sh = rule == MOD_GRAY_OPENCV3 ? 14 : 15;
+        for (uint32_t r = 0; r < h; r++)
+          for (uint32_t c = 0; c < w; c++) {
+            const uint8_t* p = &src.data[static_cast<size_t>(r) * src.step + c * 4];  // r, g, b, a
+            const int want = (cr * p[0] + cg * p[1] + cb * p[2] + (1 << (sh - 1))) >> sh;
+            if (mono[static_cast<size_t>(r) * w + c] != want) return fail("toMono8 pixels");
+          }
+      }
+      sensor_msgs::Image bayer = src;
+      bayer.encoding = "bayer_rggb8";
+      if (constructor.toMono8(bayer, mono)) return fail("an encoding cv_bridge converts differently was accepted");
     }
 
     FILE* o = std::fopen(argv[2], "wb");
