@@ -23,7 +23,10 @@
 //                memory and every dynamic pixel evaluates its window once.  N in 1..4 (cl_tile_fast_kernel): pixels
 //                link to one accepted neighbour (a forest, no atomics), the forest is flattened and the remaining
 //                accepted edges are settled by label compares, with unions only where labels differ.  Other N
-//                (cl_tile_kernel): implied-edge elimination, then per-edge unions in a shared-memory union-find.
+//                (cl_tile_kernel; only neighbor_distance 0 still takes it): implied-edge elimination, then per-edge unions
+//                in a shared-memory union-find.  N in 5..10 (cl_tile_wide_kernel, cluster_wide.cuh): the halo pixels are
+//                nodes of the tile's union-find, labels are compared before depth gates are evaluated, and every halo
+//                pixel that joined a component yields one (halo pixel, tile root) pair for cl_merge_pairs.
 //                The tile then publishes parent[pixel] = tile root, per-tile-root partial statistics (size,
 //                reference-order key, min/max of x,y,z; warp-shuffle reduced, then atomics), and three compact lists:
 //                dynamic pixels (with |v|), pixels with an edge leaving the tile, tile roots.
@@ -256,8 +259,9 @@ constexpr uint8_t kDyn = 1;   // dynamic
 constexpr uint8_t kLeft = 2;  // edge to the left neighbour accepted  (both dynamic, depth gate passes)
 constexpr uint8_t kUp = 4;    // edge to the upper neighbour accepted
 
-// Generic tile kernel (neighbor_distance 0 and 5..10, runtime N): window_edges with the implied-edge elimination, then
-// per-edge unions in a shared-memory union-find.  neighbor_distance 1..4 (the default is 4) takes cl_tile_fast_kernel.
+// Generic tile kernel (runtime N; since round 2 only neighbor_distance 0 reaches it): window_edges with the implied-edge
+// elimination, then per-edge unions in a shared-memory union-find.  neighbor_distance 1..4 (the default is 4) takes
+// cl_tile_fast_kernel, 5..10 cl_tile_wide_kernel.
 __global__ void __launch_bounds__(kBlock)
     cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                    uint32_t* __restrict__ border_list, uint32_t* __restrict__ root_list,
