@@ -73,3 +73,23 @@ def assert_objects_match(got, want, points32, labels, tol=0.0):
         assert ng == nw, f"median speed differs: {ng} vs {nw}"
         members = pts[lab == g["id"]][:, 4:7]
         assert (members == vg[None, :]).all(axis=1).any(), "velocity is not a member of the cluster"
+
+
+def foreign_cloud_with_nonfinite_depth(w=320, h=200, seed=77, cluster_size=100):
+    """A clusterer-stress cloud as another publisher might send it: some DYNAMIC points carry z = NaN / +inf / -inf
+    (x, y alike for a few), on top of depth noise of the order of depth_diff.  comparePoints' gate is
+    "if (depthDiff > th) return" (clusterer_nodelet.cpp:205-209), so a NaN difference PASSES and an infinite one fails
+    unless the threshold is infinite too -- the tile kernels stage non-dynamic cells as z = +inf and must take their
+    explicit-flag path for such points and thresholds."""
+    from moving_object_detector_b200 import synth
+    cloud, _ = synth.make_stress_cloud(w, h, seed=seed, cluster_size=cluster_size, fx=140.0)
+    rng = np.random.RandomState(seed)
+    cloud[..., 2] += rng.normal(0.0, 0.08, (h, w)).astype(np.float32)
+    v = cloud[..., 4:7]
+    dyn = np.sqrt((v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2]) >= 0.3
+    pick = rng.rand(h, w)
+    cloud[dyn & (pick < 0.03), 2] = np.nan
+    cloud[dyn & (pick >= 0.03) & (pick < 0.04), 2] = np.inf
+    cloud[dyn & (pick >= 0.04) & (pick < 0.05), 2] = -np.inf
+    cloud[dyn & (pick >= 0.05) & (pick < 0.055), 0] = np.nan
+    return cloud

@@ -331,6 +331,24 @@ def test_every_neighbor_distance_path_matches_oracle(oracle, n, size):
         assert want["n_objects"] > 3
 
 
+@pytest.mark.parametrize("depth_diff", [0.15, float("inf"), 1e30, 0.0])
+@pytest.mark.parametrize("n", [1, 4, 7, 10])
+def test_nonfinite_depths_and_thresholds_take_the_flag_paths(oracle, n, depth_diff):
+    """Dynamic points with z = NaN / +-inf and thresholds up to +inf: the tile kernels (fast: N <= 4, halo-node: N >= 5)
+    cannot rely on "non-dynamic cells hold +inf" there and switch to their explicit-flag window evaluation; the cluster
+    map must still carry the reference's ids (the oracle is pinned to the reference build on the same clouds in
+    tests/test_reference_build.py)."""
+    from helpers import foreign_cloud_with_nonfinite_depth
+    cloud = foreign_cloud_with_nonfinite_depth()
+    h, w = cloud.shape[:2]
+    want = oracle.cluster(cloud, 100, depth_diff, 0.3, n)
+    with Context(w, h) as c:
+        got = c.cluster(cloud, ClustererConfig(cluster_size=100, depth_diff=depth_diff, neighbor_distance=n), max_objs=2048)
+    assert np.array_equal(got.labels, want["labels"])
+    assert got.n_objects == want["n_objects"]
+    assert [int(o["n_points"]) for o in got.objects] == [int(o["n_points"]) for o in want["objects"]]
+
+
 @pytest.mark.parametrize("sizes", [(131072,), (150000, 98304, 3000), (300000, 2600, 2600, 2600, 120000)])
 def test_long_member_lists_take_the_cluster_kernel_and_match_the_oracle(oracle, sizes):
     """Objects of >= 96 k members on a frame of >= 1.5 Mpx are reduced by cooperating CTAs of a thread-block cluster

@@ -237,6 +237,21 @@ def test_pipeline_through_the_published_message(oracle, ref):
         assert rc["objects"][k].tobytes() == oc["objects"][k].tobytes(), k
 
 
+@pytest.mark.parametrize("depth_diff", [0.15, float("inf"), 1e30, 0.0])
+def test_nonfinite_depths_oracle_equals_reference_labels(oracle, ref, depth_diff):
+    """Dynamic points with z = NaN / +-inf and thresholds up to +inf: dynamic map and cluster map (the reference's ids).
+    Objects are not compared: pcl::getMinMax3D on NaN coordinates depends on the member order."""
+    from helpers import foreign_cloud_with_nonfinite_depth
+    cloud = foreign_cloud_with_nonfinite_depth()
+    for n in (1, 4, 7, 10):
+        kw = dict(cluster_size=100, depth_diff=depth_diff, dynamic_speed=0.3, neighbor_distance=n)
+        o, r = oracle.cluster(cloud, **kw), ref.cluster(cloud, **kw)
+        assert r["status"] == 0
+        assert np.array_equal(o["dynamic"], r["dynamic"]), ("dynamic map", n)
+        assert np.array_equal(o["labels"], r["labels"]), ("cluster map", n)
+        assert o["n_objects"] == r["n_objects"] and (depth_diff == 0.0 or o["n_objects"] > 0)
+
+
 def test_stress_cloud_oracle_equals_reference(oracle, ref):
     """Clusterer-stress structure (serpentine, blobs straddling cluster_size, specks, checkerboards, depth steps)."""
     from moving_object_detector_b200 import synth
