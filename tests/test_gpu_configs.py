@@ -74,12 +74,15 @@ def test_kitti_scale_batch_matches_oracle(oracle):
     assert out["stats"]["n_objects"].sum() > 0
 
 
-def test_zed_720p_batch_matches_oracle(oracle):
-    """config 2, the benchmark workload, through the device-resident batched calls the benchmark times."""
+@pytest.mark.parametrize("n", [4, 2, 7, 10])
+def test_zed_720p_batch_matches_oracle(oracle, n):
+    """config 2, the benchmark workload, through the device-resident batched calls the benchmark times; besides the
+    default neighbor_distance also 2 (another fast-kernel instantiation) and 7 / 10 (the halo-node kernel on the noisy
+    depth of the benchmark sequence, where about half of the window's depth gates fail)."""
     cfg = synth.CONFIGS["zed_1280x720"]
-    B = 3
+    B = 3 if n == 4 else 2
     seq = synth.make_sequence(cfg, B + 1)
-    cl = ClustererConfig()
+    cl = ClustererConfig(neighbor_distance=n)
     out = _run_batched(seq, cfg, B, cl)
     _check_batch_against_oracle(oracle, seq, out, B, cl)
     assert out["stats"]["n_objects"].min() >= 2
@@ -97,7 +100,7 @@ def test_uhd_frame_matches_oracle(oracle):
 @pytest.mark.parametrize("n", [1, 4, 10])
 def test_hd2k_clusterer_stress_matches_oracle(oracle, n):
     """config 4: 2208x1242 with ~45 % dynamic pixels -- serpentine, blobs straddling cluster_size, specks,
-    checkerboards, depth steps -- at neighbor_distance 1 (fast path), 4 (default), 10 (generic path)."""
+    checkerboards, depth steps -- at neighbor_distance 1 (fast kernel), 4 (default), 10 (halo-node kernel)."""
     cloud, dyn = synth.make_stress_cloud(2208, 1242)
     cfg = ClustererConfig(cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=n)
     want = oracle.cluster(cloud, 2500, 0.15, 0.3, n)
