@@ -265,9 +265,25 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
   for (int k = threadIdx.x; k < kCells; k += kBlock) s_rep[k] = kNone;  // the second-cell slots are free now
   __syncthreads();
 
+  // One component in the tile (the usual case inside a blob and on smooth depth): every core pixel and every halo pixel
+  // that joined carries the same label, so every accepted edge joins equal labels and C2 has nothing to find.  A halo
+  // pixel that did NOT join (label = itself: halo pixels are leaves or singletons, never parents) has no accepted edge
+  // into this tile's core -- H scanned all of its candidates -- and is ignored.
+  bool one_label = true;
+  {
+    const int first = s_lab[s_dl[nd >> 1]];
+    for (int e = threadIdx.x; e < nd; e += kBlock) one_label = one_label && (s_lab[s_dl[e]] == first);
+    for (int k = threadIdx.x; k < kHalo; k += kBlock) {
+      const int h = halo_cell(k);
+      const int l = s_lab[h];
+      one_label = one_label && (l < 0 || l == h || l == first);
+    }
+  }
+  const bool skip_compare = __syncthreads_and(one_label);
+
   // C2: compare labels over the whole window; depth gates only where a foreign label shows up
   bool unioned = false;
-  for (int e0 = 0; e0 < nd; e0 += kBlock) {
+  for (int e0 = 0; e0 < (skip_compare ? 0 : nd); e0 += kBlock) {
     const int e = e0 + threadIdx.x;
     int p = kCore, my = 0;
     float z_here = 0.0f;
