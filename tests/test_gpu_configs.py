@@ -384,3 +384,36 @@ def test_long_member_lists_take_the_cluster_kernel_and_match_the_oracle(oracle, 
         got = c.cluster(cloud, want_labels=True)
     assert np.array_equal(got.labels, want["labels"])
     assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
+
+
+def test_long_object_queues_match_the_oracle(oracle):
+    """A batch with ~950 objects (more than three rounds of cl_objects' one-CTA-per-object work queue): many small blobs
+    around cluster_size, member lists shorter and longer than the shared-memory staging, coarse speeds (ties at the
+    median) -- every frame's labels and objects against the oracle."""
+    import torch
+    from moving_object_detector_b200.api import OBJECT_DTYPE, STATS_DTYPE
+    W, H, B, MAXO = 640, 400, 10, 512
+    clouds = [synth.make_stress_cloud(W, H, seed=900 + i, cluster_size=50)[0] for i in range(B)]
+    for c in clouds:  # a few big members lists beside the small blobs: the serpentine already has > 2048 members
+        c[..., 4:7] = np.round(c[..., 4:7] * 8) / 8   # coarse speeds: many ties at the median
+    cfg = ClustererConfig(cluster_size=40, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=3)
+    wants = [oracle.cluster(c, 40, 0.15, 0.3, 3) for c in clouds]
+    total = sum(w["n_objects"] for w in wants)
+    assert total >= 3 * 2 * 148, total
+    assert max(int(o["n_points"]) for w in wants for o in w["objects"]) > 2048
+    pts = torch.from_numpy(np.stack(clouds).reshape(B, H * W, 8)).cuda()
+    lab = torch.empty((B, H * W), dtype=torch.int32, device="cuda")
+    objs = torch.zeros((B, MAXO * OBJECT_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    stats = torch.zeros((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    with Context(W, H, max_batch=B) as c:
+        c.cluster_batched_dev(W, H, B, pts, None, cfg, objs, stats, MAXO, labels=lab,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    labels = lab.cpu().numpy().reshape(B, H, W)
+    o = objs.cpu().numpy().view(OBJECT_DTYPE).reshape(B, MAXO)
+    st = stats.cpu().numpy().view(STATS_DTYPE).reshape(B)
+    for i in range(B):
+        assert np.array_equal(labels[i], wants[i]["labels"]), i
+        n = int(st[i]["n_objects"])
+        assert n == wants[i]["n_objects"] and st[i]["status"] == 0
+        assert_objects_match(o[i][:n], wants[i]["objects"], clouds[i], wants[i]["labels"])
