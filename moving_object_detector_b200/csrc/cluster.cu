@@ -1407,6 +1407,45 @@ __device__ __forceinline__ int obj_tie_break(const uint32_t* speeds, const int* 
   return best;
 }
 
+// Copies the members of a global list whose speed matches `prefix` in its `himask` bits -- the candidates the first two
+// radix passes left -- into shared memory (speed bits and pixel index, any order).  The caller knows their number (the
+// selected bin's count) and only calls this when they fit.
+template <int kThreads>
+__device__ __forceinline__ void obj_collect(const uint32_t* speeds, const int* pixels, int n, uint32_t himask,
+                                            uint32_t prefix, uint32_t* c_speed, int* c_pixel, int* counter) {
+  const int tid = threadIdx.x;
+  auto take = [&](uint32_t v, int j) {
+    if ((v & himask) == prefix) {
+      const int pos = atomicAdd(counter, 1);
+      c_speed[pos] = v;
+      c_pixel[pos] = pixels[j];
+    }
+  };
+  const ObjSplit sp = obj_split(speeds, n);
+  {
+    int j = -1;
+    if (tid < sp.head) j = tid;
+    else if (tid - sp.head < n - sp.tail0) j = sp.tail0 + (tid - sp.head);
+    if (j >= 0) take(__ldcg(speeds + j), j);
+  }
+  const uint4* vec = reinterpret_cast<const uint4*>(speeds + sp.head);
+  for (int i0 = 0; i0 < sp.nvec; i0 += 2 * kThreads) {
+    const int ia = i0 + tid, ib = ia + kThreads;
+    uint4 a = make_uint4(~prefix, ~prefix, ~prefix, ~prefix), b = a;  // ~prefix never matches (himask != 0)
+    if (ia < sp.nvec) a = __ldcg(vec + ia);
+    if (ib < sp.nvec) b = __ldcg(vec + ib);
+    const int ja = sp.head + 4 * ia, jb = sp.head + 4 * ib;
+    take(a.x, ja);
+    take(a.y, ja + 1);
+    take(a.z, ja + 2);
+    take(a.w, ja + 3);
+    take(b.x, jb);
+    take(b.y, jb + 1);
+    take(b.z, jb + 2);
+    take(b.w, jb + 3);
+  }
+}
+
 template <bool kClustersPossible>  // false: the instantiation small frames run never looks at the choice
 __global__ void __launch_bounds__(kObjBlock, 2)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
@@ -1419,6 +1458,8 @@ __global__ void __launch_bounds__(kObjBlock, 2)
   __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_k;
   __shared__ int s_best;
+  __shared__ unsigned s_sel;  // members in the bin the last pass selected
+  __shared__ int s_cn;
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const int n_work = *work_count;
   if constexpr (kClustersPossible) {
@@ -1433,18 +1474,21 @@ __global__ void __launch_bounds__(kObjBlock, 2)
     const int2 w = work_items[item];
     const int frame = w.x, slot = w.y;
     ClusterStat& st = L.stats[static_cast<size_t>(frame) * L.max_clusters + slot];
-    const int n = st.count;
     const size_t off = frame * P + member_offset[static_cast<size_t>(frame) * L.max_clusters + slot];
     const uint32_t* gspeeds = member_speed + off;
-    const int* pixels = member_pixel + off;
-    const bool staged = n <= kSmemMembers;
+    const int* gpixels = member_pixel + off;
+    const int n_all = st.count;
+    bool staged = n_all <= kSmemMembers;
     if (staged)
-      for (int j = threadIdx.x; j < n; j += kObjBlock) s_speed[j] = gspeeds[j];
+      for (int j = threadIdx.x; j < n_all; j += kObjBlock) s_speed[j] = gspeeds[j];
     const uint32_t* speeds = staged ? s_speed : gspeeds;
+    const int* pixels = gpixels;
+    int n = n_all;  // members the passes walk: the whole list, or the candidates collected after the second pass
     if (threadIdx.x == 0) {
       s_prefix = 0;
       s_k = static_cast<uint32_t>(n / 2);  // cluster.at(cluster.size() / 2) after the descending sort
       s_best = 0x7fffffff;
+      s_cn = 0;
     }
     int decided = 0;  // number of high bits already fixed
     for (int pass = 0; pass < 3; pass++) {
@@ -1455,6 +1499,23 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       const uint32_t prefix = s_prefix;
       const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
       const uint32_t binmask = (1u << bits) - 1u;
+#ifndef CL_OBJECTS_COLLECT
+#define CL_OBJECTS_COLLECT 1
+#endif
+      if (CL_OBJECTS_COLLECT && pass == 2 && !staged && s_sel <= kSmemMembers / 2) {
+        // A list that streams from global memory: 22 bits are decided and the selected bin's members (a handful unless
+        // thousands tie) are all that the last pass and the tie-break still look at.  One more walk over the list
+        // copies them into the (unused) staging buffer; the last pass and the tie-break then run on shared memory
+        // instead of walking the list twice more.
+        uint32_t* c_speed = s_speed;
+        int* c_pixel = reinterpret_cast<int*>(s_speed + kSmemMembers / 2);
+        obj_collect<kObjBlock>(gspeeds, gpixels, n_all, himask, prefix, c_speed, c_pixel, &s_cn);
+        __syncthreads();
+        n = s_cn;
+        speeds = c_speed;
+        pixels = c_pixel;
+        staged = true;
+      }
       obj_hist_pass<kObjBlock>(hist, speeds, n, !staged, himask, prefix, shift, binmask);
       __syncthreads();
       // parallel suffix scan: thread t owns bins hi = kBins-1-2t and hi-1 (descending order, k counts from the top)
@@ -1485,9 +1546,11 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       if (k >= before && k < before + h0) {
         s_k = k - before;
         s_prefix = prefix | (static_cast<uint32_t>(hi) << shift);
+        s_sel = h0;
       } else if (k >= before + h0 && k < before + h0 + h1) {
         s_k = k - before - h0;
         s_prefix = prefix | (static_cast<uint32_t>(hi - 1) << shift);
+        s_sel = h1;
       }
       decided += bits;
       __syncthreads();
@@ -1513,7 +1576,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
           o.center[k] = __fdiv_rn(__fadd_rn(mn, mx), 2.0f);
           o.velocity[k] = rec[4 + k];
         }
-        o.n_points = n;
+        o.n_points = n_all;
         L.objs[static_cast<size_t>(frame) * L.max_objs + id] = o;
       }
     }

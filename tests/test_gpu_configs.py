@@ -417,3 +417,44 @@ def test_long_object_queues_match_the_oracle(oracle):
         n = int(st[i]["n_objects"])
         assert n == wants[i]["n_objects"] and st[i]["status"] == 0
         assert_objects_match(o[i][:n], wants[i]["objects"], clouds[i], wants[i]["labels"])
+
+
+@pytest.mark.parametrize("tie_fraction", [0.0, 0.1, 0.4])
+def test_streamed_member_lists_candidates_and_ties(oracle, tie_fraction):
+    """Objects whose member lists do not fit cl_objects' shared-memory staging (> 9216 members) on a frame below the
+    thread-block-cluster threshold: after two radix passes the candidates of the selected bin are copied to shared
+    memory (a handful; ~1000 and ~2000 tied members at the median for tie_fraction 0.1) -- or, when more than 4608
+    members tie at the median (tie_fraction 0.4 of 20000 and 30000), the passes keep walking the global list."""
+    W, H = 1024, 512
+    rng = np.random.RandomState(int(tie_fraction * 100) + 3)
+    cloud = np.zeros((H, W, 8), np.float32)
+    cloud[..., 2] = 5.0
+    cloud[..., 0] = (np.arange(W, dtype=np.float32) - W / 2)[None, :] * 0.01
+    cloud[..., 1] = (np.arange(H, dtype=np.float32) - H / 2)[:, None] * 0.01
+    sizes = (20000, 30000, 9300, 4000)
+    y0 = 8
+    for k, n in enumerate(sizes):
+        bw = 1000 if n > 9000 else 100
+        bh = -(-n // bw)
+        assert y0 + bh + 8 < H
+        ys, xs = np.divmod(np.arange(n), bw)
+        speed = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        n_tie = int(tie_fraction * n)
+        if n_tie:
+            # the tied value sits at the median: as many faster as slower members around it
+            speed[:n_tie] = np.float32(1.25)
+            rest = n - n_tie
+            speed[n_tie:n_tie + rest // 2] = rng.uniform(1.3, 2.0, rest // 2).astype(np.float32)
+            speed[n_tie + rest // 2:] = rng.uniform(0.5, 1.2, rest - rest // 2).astype(np.float32)
+            speed = speed[rng.permutation(n)]
+        ang = rng.uniform(0, 2 * np.pi, n)
+        cloud[y0 + ys, 8 + xs, 4] = speed * np.cos(ang).astype(np.float32)
+        cloud[y0 + ys, 8 + xs, 5] = speed * np.sin(ang).astype(np.float32)
+        cloud[y0 + ys, 8 + xs, 2] = 5.0 + 0.001 * k
+        y0 += bh + 12
+    want = oracle.cluster(cloud)
+    assert want["n_objects"] == len(sizes)
+    with Context(W, H) as c:
+        got = c.cluster(cloud, want_labels=True)
+    assert np.array_equal(got.labels, want["labels"])
+    assert_objects_match(got.objects, want["objects"], cloud, want["labels"])
