@@ -1605,10 +1605,13 @@ __global__ void __launch_bounds__(kObjBlock, 2)
   __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_k;
   __shared__ int s_best;
+  __shared__ unsigned s_sel;  // rank 0: members (of the whole object) in the bin the last pass selected
+  __shared__ int s_cn;        // this CTA's collected candidates
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const int* item0 = cluster.map_shared_rank(&s_item, 0);
   const uint32_t* prefix0 = cluster.map_shared_rank(&s_prefix, 0);
+  const unsigned* sel0 = cluster.map_shared_rank(&s_sel, 0);
   int* best0 = cluster.map_shared_rank(&s_best, 0);
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const int n_work = *work_count;
@@ -1639,13 +1642,16 @@ __global__ void __launch_bounds__(kObjBlock, 2)
     // this CTA's slice of the member list
     const int len = (n + kC - 1) / kC;
     const int begin = min(n, static_cast<int>(crank) * len), end = min(n, begin + len);
-    const int m = end - begin;
+    const int m_all = end - begin;
+    int m = m_all;  // members the passes walk: the slice, or its candidates collected after the second pass
     const uint32_t* gspeeds = member_speed + off + begin;
-    const int* pixels = member_pixel + off + begin;
-    const bool staged = m <= kSmemMembers;
+    const int* gpixels = member_pixel + off + begin;
+    const int* pixels = gpixels;
+    bool staged = m <= kSmemMembers;
     if (staged)
       for (int j = threadIdx.x; j < m; j += kObjBlock) s_speed[j] = gspeeds[j];
     const uint32_t* speeds = staged ? s_speed : gspeeds;
+    if (threadIdx.x == 0) s_cn = 0;  // ordered before its use by the barriers of the first two passes
     int decided = 0;  // number of high bits already fixed
     for (int pass = 0; pass < 3; pass++) {
       const int bits = pass < 2 ? 11 : 10;
@@ -1655,6 +1661,18 @@ __global__ void __launch_bounds__(kObjBlock, 2)
       const uint32_t prefix = *prefix0;
       const uint32_t himask = decided == 0 ? 0u : (0xffffffffu << (32 - decided));
       const uint32_t binmask = (1u << bits) - 1u;
+      if (CL_OBJECTS_COLLECT && pass == 2 && !staged && *sel0 <= kSmemMembers / 2) {
+        // as in cl_objects_kernel: this CTA's candidates of the selected bin move to shared memory, the last pass and
+        // the tie-break run there (the whole object's bin count bounds every slice's share)
+        uint32_t* c_speed = s_speed;
+        int* c_pixel = reinterpret_cast<int*>(s_speed + kSmemMembers / 2);
+        obj_collect<kObjBlock>(gspeeds, gpixels, m_all, himask, prefix, c_speed, c_pixel, &s_cn);
+        __syncthreads();
+        m = s_cn;
+        speeds = c_speed;
+        pixels = c_pixel;
+        staged = true;
+      }
       obj_hist_pass<kObjBlock>(hist, speeds, m, !staged, himask, prefix, shift, binmask);
       cluster.sync();  // every CTA's histogram is complete
       if (crank == 0) {
@@ -1692,9 +1710,11 @@ __global__ void __launch_bounds__(kObjBlock, 2)
         if (k >= before && k < before + h0) {
           s_k = k - before;
           s_prefix = prefix | (static_cast<uint32_t>(hi) << shift);
+          s_sel = h0;
         } else if (k >= before + h0 && k < before + h0 + h1) {
           s_k = k - before - h0;
           s_prefix = prefix | (static_cast<uint32_t>(hi - 1) << shift);
+          s_sel = h1;
         }
       }
       decided += bits;
