@@ -1298,19 +1298,25 @@ __device__ __forceinline__ bool objects_use_clusters(const ClLaunch& L, int n_wo
 // memory staging stream from global memory (L2: cl_scatter has just written them), and a pass over a 30 k list by 1024
 // threads is only a handful of iterations, so its time is load latency, not bandwidth: the streaming form reads the
 // list as 16-byte vectors, two in flight per thread (eight members), after a scalar head that aligns the pointer.
+#ifndef CL_OBJECTS_MATCH_FIRST_ONLY
+#define CL_OBJECTS_MATCH_FIRST_ONLY 1
+#endif
+template <bool kTryUniform>
 __device__ __forceinline__ void obj_count(unsigned* hist, uint32_t v, bool ok, uint32_t himask, uint32_t prefix, int shift,
                                           uint32_t binmask, int lane) {
   int bin = -1;
   if (ok && (v & himask) == prefix) bin = static_cast<int>((v >> shift) & binmask);
   // members of one object move alike: in the first pass nearly every warp is uniform (one atomic per warp);
   // later passes spread over the bins and plain shared-memory atomics are cheaper than a match
-  int uniform;
-  __match_all_sync(kFull, bin, &uniform);
-  if (uniform) {
-    if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
-  } else if (bin >= 0) {
-    atomicAdd(&hist[bin], 1u);
+  if constexpr (kTryUniform) {
+    int uniform;
+    __match_all_sync(kFull, bin, &uniform);
+    if (uniform) {
+      if (bin >= 0 && lane == 0) atomicAdd(&hist[bin], 32u);
+      return;
+    }
   }
+  if (bin >= 0) atomicAdd(&hist[bin], 1u);
 }
 
 // head / vector split of a global list of n 32-bit entries: [0, head) scalar, nvec uint4 from head, then a scalar tail
@@ -1326,7 +1332,7 @@ __device__ __forceinline__ ObjSplit obj_split(const void* p, int n) {
 }
 
 // One histogram pass over the list (every thread of the CTA calls it: the match in obj_count is warp-wide).
-template <int kThreads>
+template <int kThreads, bool kTryUniform = true>
 __device__ __forceinline__ void obj_hist_pass(unsigned* hist, const uint32_t* speeds, int n, bool in_global,
                                               uint32_t himask, uint32_t prefix, int shift, uint32_t binmask) {
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1341,7 +1347,7 @@ __device__ __forceinline__ void obj_hist_pass(unsigned* hist, const uint32_t* sp
         v[q] = ok[q] ? speeds[j] : 0u;
       }
 #pragma unroll
-      for (int q = 0; q < 4; q++) obj_count(hist, v[q], ok[q], himask, prefix, shift, binmask, lane);
+      for (int q = 0; q < 4; q++) obj_count<kTryUniform>(hist, v[q], ok[q], himask, prefix, shift, binmask, lane);
     }
     return;
   }
@@ -1350,7 +1356,7 @@ __device__ __forceinline__ void obj_hist_pass(unsigned* hist, const uint32_t* sp
     int j = -1;
     if (tid < sp.head) j = tid;
     else if (tid - sp.head < n - sp.tail0) j = sp.tail0 + (tid - sp.head);
-    obj_count(hist, j >= 0 ? __ldcg(speeds + j) : 0u, j >= 0, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, j >= 0 ? __ldcg(speeds + j) : 0u, j >= 0, himask, prefix, shift, binmask, lane);
   }
   const uint4* vec = reinterpret_cast<const uint4*>(speeds + sp.head);
   for (int i0 = 0; i0 < sp.nvec; i0 += 2 * kThreads) {
@@ -1359,14 +1365,14 @@ __device__ __forceinline__ void obj_hist_pass(unsigned* hist, const uint32_t* sp
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
     if (oka) a = __ldcg(vec + ia);
     if (okb) b = __ldcg(vec + ib);
-    obj_count(hist, a.x, oka, himask, prefix, shift, binmask, lane);
-    obj_count(hist, a.y, oka, himask, prefix, shift, binmask, lane);
-    obj_count(hist, a.z, oka, himask, prefix, shift, binmask, lane);
-    obj_count(hist, a.w, oka, himask, prefix, shift, binmask, lane);
-    obj_count(hist, b.x, okb, himask, prefix, shift, binmask, lane);
-    obj_count(hist, b.y, okb, himask, prefix, shift, binmask, lane);
-    obj_count(hist, b.z, okb, himask, prefix, shift, binmask, lane);
-    obj_count(hist, b.w, okb, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, a.x, oka, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, a.y, oka, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, a.z, oka, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, a.w, oka, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, b.x, okb, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, b.y, okb, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, b.z, okb, himask, prefix, shift, binmask, lane);
+    obj_count<kTryUniform>(hist, b.w, okb, himask, prefix, shift, binmask, lane);
   }
 }
 
@@ -1516,7 +1522,10 @@ __global__ void __launch_bounds__(kObjBlock, 2)
         pixels = c_pixel;
         staged = true;
       }
-      obj_hist_pass<kObjBlock>(hist, speeds, n, !staged, himask, prefix, shift, binmask);
+      if (CL_OBJECTS_MATCH_FIRST_ONLY && pass > 0)
+        obj_hist_pass<kObjBlock, false>(hist, speeds, n, !staged, himask, prefix, shift, binmask);
+      else
+        obj_hist_pass<kObjBlock, true>(hist, speeds, n, !staged, himask, prefix, shift, binmask);
       __syncthreads();
       // parallel suffix scan: thread t owns bins hi = kBins-1-2t and hi-1 (descending order, k counts from the top)
       const int hi = kBins - 1 - 2 * static_cast<int>(threadIdx.x);
@@ -1673,7 +1682,10 @@ __global__ void __launch_bounds__(kObjBlock, 2)
         pixels = c_pixel;
         staged = true;
       }
-      obj_hist_pass<kObjBlock>(hist, speeds, m, !staged, himask, prefix, shift, binmask);
+      if (CL_OBJECTS_MATCH_FIRST_ONLY && pass > 0)
+        obj_hist_pass<kObjBlock, false>(hist, speeds, m, !staged, himask, prefix, shift, binmask);
+      else
+        obj_hist_pass<kObjBlock, true>(hist, speeds, m, !staged, himask, prefix, shift, binmask);
       cluster.sync();  // every CTA's histogram is complete
       if (crank == 0) {
         // parallel suffix scan over the summed histograms: thread t owns bins hi = kBins-1-2t and hi-1
