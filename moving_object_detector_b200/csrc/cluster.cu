@@ -57,6 +57,37 @@ constexpr int kListGrid = 148 * 8;  // grid-stride kernels over the dynamic-pixe
 
 // ---- helpers ---------------------------------------------------------------------------------------------------
 
+// Programmatic dependent launch (sm_90+): the clusterer is a chain of nine short kernels, each consuming what the
+// previous one wrote.  Every kernel of the chain starts with pdl_enter(): it lets the NEXT kernel's CTAs be scheduled as
+// soon as SM resources free up (their launch latency and prologue overlap this kernel's tail) and then waits until the
+// PREVIOUS kernel has completed and its writes are visible -- so nothing is read early, and completion stays
+// transitive along the chain.  Kernels launched without the attribute (launch_chain below with CL_PDL = 0, or <<<>>>)
+// see both instructions as no-ops.
+#ifndef CL_PDL
+#define CL_PDL 1
+#endif
+__device__ __forceinline__ void pdl_enter() {
+#if CL_PDL
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL_PDL ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -266,6 +297,7 @@ __global__ void __launch_bounds__(kBlock)
     cl_tile_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                    uint32_t* __restrict__ border_list, uint32_t* __restrict__ root_list,
                    int* __restrict__ counters /* list, border, root */) {
+  pdl_enter();
   constexpr int NC = 0;
   constexpr int kMaxN = 10;
   constexpr int HN = kMaxN;        // halo capacity
@@ -515,6 +547,7 @@ __global__ void __launch_bounds__(kBlock, CL_TILE_MIN_BLOCKS)
     cl_tile_fast_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                         uint32_t* __restrict__ border_list, uint32_t* __restrict__ border_mask,
                         uint32_t* __restrict__ root_list, int* __restrict__ counters /* list, border, root */) {
+  pdl_enter();
   static_assert(NC >= 1 && NC <= 4, "fast path covers neighbor_distance 1..4");
   constexpr int S = NC + 1;
   constexpr int SW = kTileW + NC;  // shared-memory row pitch
@@ -1004,6 +1037,7 @@ template <int NC>
 __global__ void __launch_bounds__(kBlock)
     cl_merge_kernel(const ClLaunch L, const uint32_t* __restrict__ border_list,
                     const uint32_t* __restrict__ border_mask, const int* __restrict__ border_count) {
+  pdl_enter();
   const int n = *border_count;
   const int N = NC > 0 ? NC : L.n;
   const int stride = N + 1;
@@ -1076,6 +1110,7 @@ __global__ void __launch_bounds__(kBlock)
 // into R's.  After this kernel every dynamic pixel reaches its final root in two hops (pixel -> tile root -> R).
 __global__ void __launch_bounds__(kBlock)
     cl_roots_kernel(const ClLaunch L, const uint32_t* __restrict__ root_list, const int* __restrict__ root_count) {
+  pdl_enter();
   const int n = *root_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   for (int t0 = blockIdx.x * kBlock; t0 < n; t0 += gridDim.x * kBlock) {
@@ -1109,6 +1144,7 @@ __global__ void __launch_bounds__(kBlock)
 // stored over count[R] (the size moves into the slot's ClusterStat together with the merged statistics).
 __global__ void __launch_bounds__(kBlock)
     cl_slots_kernel(const ClLaunch L, const uint32_t* __restrict__ root_list, const int* __restrict__ root_count) {
+  pdl_enter();
   const int n = *root_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   for (int t = blockIdx.x * kBlock + threadIdx.x; t < n; t += gridDim.x * kBlock) {
@@ -1147,6 +1183,7 @@ __global__ void __launch_bounds__(kBlock)
 __global__ void __launch_bounds__(kBlock)
     cl_rank_kernel(const ClLaunch L, int* __restrict__ work_count, int2* __restrict__ work_items,
                    int* __restrict__ member_offset) {
+  pdl_enter();
   extern __shared__ int s_keys[];  // [n]
   __shared__ int s_part[kBlock];
   __shared__ int s_base;
@@ -1203,6 +1240,7 @@ __global__ void __launch_bounds__(kBlock)
                       const int* __restrict__ list_count,
                       const int* __restrict__ member_offset, int* __restrict__ cursor,
                       uint32_t* __restrict__ member_speed, int* __restrict__ member_pixel) {
+  pdl_enter();
   const int n = *list_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   const int lane = threadIdx.x & 31;
@@ -1457,6 +1495,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
     cl_objects_kernel(const ClLaunch L, const int* __restrict__ work_count, const int2* __restrict__ work_items,
                       int* __restrict__ work_cursor, const int* __restrict__ member_offset,
                       const uint32_t* __restrict__ member_speed, const int* __restrict__ member_pixel) {
+  pdl_enter();
   __shared__ uint32_t s_speed[kSmemMembers];
   __shared__ unsigned hist[kBins];
   __shared__ unsigned s_wsum[kObjBlock / 32];
@@ -1607,6 +1646,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
                               const int2* __restrict__ work_items, int* __restrict__ work_cursor,
                               const int* __restrict__ member_offset, const uint32_t* __restrict__ member_speed,
                               const int* __restrict__ member_pixel) {
+  pdl_enter();
   __shared__ uint32_t s_speed[kSmemMembers];
   __shared__ unsigned hist[kBins];
   __shared__ unsigned s_wsum[kObjBlock / 32];
@@ -1764,6 +1804,7 @@ __global__ void __launch_bounds__(kObjBlock, 2)
 // ---- cl_labels --------------------------------------------------------------------------------------------------
 // Final cluster_map_ (after removeSmallClusters' relabel, :386-392), dense, -1 = NOT_BELONGED_.
 __global__ void __launch_bounds__(kBlock) cl_labels_kernel(const ClLaunch L) {
+  pdl_enter();
   const size_t P = static_cast<size_t>(L.w) * L.h;
   const size_t total = P * L.batch;
   for (size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; g < total;
@@ -1806,6 +1847,7 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 __global__ void cl_reset_kernel(int* a, size_t na, int* b, size_t nb, int* c, size_t nc) {
+  pdl_enter();
   const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (t < na) a[t] = 0;
   if (t < nb) b[t] = 0;
@@ -1833,9 +1875,9 @@ void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint
                        int* counters) {
   const dim3 tgrid((L.w + kTileW - 1) / kTileW, (L.h + kTileH - 1) / kTileH, L.batch);
   if constexpr (NC > 4) {
-    cl_tile_wide_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
-                                                     counters);
-    cl_merge_pairs_kernel<<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
+    launch_chain(cl_tile_wide_kernel<NC>, tgrid, dim3(kBlock), 0, s, L, X.list, X.list_speed, border_list, X.border_mask,
+                 root_list, counters);
+    launch_chain(cl_merge_pairs_kernel, dim3(kListGrid), dim3(kBlock), 0, s, L, border_list, X.border_mask, counters + 1);
     return;
   } else if constexpr (NC > 0) {
     const int choice = tile_kernel_choice();
@@ -1846,8 +1888,8 @@ void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint
       return;
     }
     if (choice == 0) {
-      cl_tile_fast_kernel<NC><<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, X.border_mask, root_list,
-                                                       counters);
+      launch_chain(cl_tile_fast_kernel<NC>, tgrid, dim3(kBlock), 0, s, L, X.list, X.list_speed, border_list, X.border_mask,
+                   root_list, counters);
     } else {
       const int tiles_x = (L.w + (32 - NC) - 1) / (32 - NC);
       const dim3 sgrid((tiles_x + CL_SCAN_WARPS - 1) / CL_SCAN_WARPS, (L.h + CL_SCAN_ROWS - 1) / CL_SCAN_ROWS, L.batch);
@@ -1857,7 +1899,7 @@ void launch_tile_merge(cudaStream_t s, const ClLaunch& L, const ClExtra& X, uint
   } else {
     cl_tile_kernel<<<tgrid, kBlock, 0, s>>>(L, X.list, X.list_speed, border_list, root_list, counters);
   }
-  cl_merge_kernel<NC><<<kListGrid, kBlock, 0, s>>>(L, border_list, X.border_mask, counters + 1);
+  launch_chain(cl_merge_kernel<NC>, dim3(kListGrid), dim3(kBlock), 0, s, L, border_list, X.border_mask, counters + 1);
 }
 
 }  // namespace
@@ -1891,6 +1933,8 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
     // zero n_slots / n_dynamic (adjacent, 2*batch), cursor (batch*max_clusters), and the five counters
     // work_count, work_cursor, list_count, border_count, root_count
     const size_t m = n_cs > 2 * n_fs ? n_cs : 2 * n_fs;
+    // an ordinary launch: the chain starts here (extending it backwards -- this kernel dependent on the scene-flow
+    // kernel, which then releases its dependents early -- measured +1 us on the scene-flow kernel and nothing here)
     cl_reset_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, s>>>(L.n_slots, 2 * n_fs, X.cursor, n_cs,
                                                                           X.work_count, 5);
   }
@@ -1911,24 +1955,24 @@ cudaError_t launch_cluster(cudaStream_t s, const ClLaunch& L, const ClExtra& X, 
     case 10: launch_tile_merge<10>(s, L, X, border_list, root_list, counters); break;
     default: launch_tile_merge<0>(s, L, X, border_list, root_list, counters); break;
   }
-  cl_roots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
-  cl_slots_kernel<<<kListGrid, kBlock, 0, s>>>(L, root_list, counters + 2);
+  launch_chain(cl_roots_kernel, dim3(kListGrid), dim3(kBlock), 0, s, L, root_list, counters + 2);
+  launch_chain(cl_slots_kernel, dim3(kListGrid), dim3(kBlock), 0, s, L, root_list, counters + 2);
   const size_t rank_smem = static_cast<size_t>(L.max_clusters) * sizeof(int);
   if (rank_smem > 48 * 1024) {  // contexts created for more than 12288 clusters per frame: opt in to the larger table
     const cudaError_t e = cudaFuncSetAttribute(cl_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                static_cast<int>(rank_smem));
     if (e != cudaSuccess) return e;
   }
-  cl_rank_kernel<<<L.batch, kBlock, rank_smem, s>>>(L, X.work_count, X.work_items, X.member_offset);
-  cl_scatter_kernel<<<kListGrid, kBlock, 0, s>>>(L, X.list, X.list_speed, counters, X.member_offset, X.cursor, X.member_speed,
-                                                 X.member_pixel);
+  launch_chain(cl_rank_kernel, dim3(L.batch), dim3(kBlock), rank_smem, s, L, X.work_count, X.work_items, X.member_offset);
+  launch_chain(cl_scatter_kernel, dim3(kListGrid), dim3(kBlock), 0, s, L, X.list, X.list_speed, counters, X.member_offset,
+               X.cursor, X.member_speed, X.member_pixel);
   const bool clusters_possible = static_cast<size_t>(L.w) * L.h >= kObjClusterMinPixels;
   if (!clusters_possible) {
-    cl_objects_kernel<false><<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
-                                                       X.member_speed, X.member_pixel);
+    launch_chain(cl_objects_kernel<false>, dim3(2 * 148), dim3(kObjBlock), 0, s, L, X.work_count, X.work_items,
+                 X.work_cursor, X.member_offset, X.member_speed, X.member_pixel);
   } else {  // plus the thread-block-cluster variant; exactly one of the two processes the batch
-    cl_objects_kernel<true><<<2 * 148, kObjBlock, 0, s>>>(L, X.work_count, X.work_items, X.work_cursor, X.member_offset,
-                                                      X.member_speed, X.member_pixel);
+    launch_chain(cl_objects_kernel<true>, dim3(2 * 148), dim3(kObjBlock), 0, s, L, X.work_count, X.work_items,
+                 X.work_cursor, X.member_offset, X.member_speed, X.member_pixel);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * 148 / kObjCluster * kObjCluster);
     cfg.blockDim = dim3(kObjBlock);

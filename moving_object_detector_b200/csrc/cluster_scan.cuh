@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(CL_SCAN_WARPS * 32, CL_SCAN_MIN_BLOCKS)
     cl_scan_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                    uint32_t* __restrict__ border_list, uint32_t* __restrict__ border_mask,
                    uint32_t* __restrict__ root_list, int* __restrict__ counters /* list, border, root */) {
+  pdl_enter();
   static_assert(NC >= 1 && NC <= 4, "one-word window masks cover neighbor_distance 1..4");
   constexpr int S = NC + 1;
   constexpr int CW = 32 - NC;        // core columns of a tile

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
     cl_tile_wide_kernel(const ClLaunch L, uint32_t* __restrict__ list, uint32_t* __restrict__ list_speed,
                         uint32_t* __restrict__ pair_halo, uint32_t* __restrict__ pair_rep,
                         uint32_t* __restrict__ root_list, int* __restrict__ counters /* list, pairs, root */) {
+  pdl_enter();
   static_assert(NC >= 1 && NC <= kClMaxNeighborDistance, "window of up to 11 x 11 cells");
   constexpr int S = NC + 1;
   constexpr int SW = kTileW + NC;  // staged row pitch
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(kBlock, CL_WIDE_MIN_BLOCKS)
 __global__ void __launch_bounds__(kBlock)
     cl_merge_pairs_kernel(const ClLaunch L, const uint32_t* __restrict__ pair_halo, const uint32_t* __restrict__ pair_rep,
                           const int* __restrict__ pair_count) {
+  pdl_enter();
   const int n = *pair_count;
   const uint32_t P = static_cast<uint32_t>(L.w) * L.h;
   for (int t0 = blockIdx.x * kBlock; t0 < n; t0 += gridDim.x * kBlock) {
