@@ -343,7 +343,7 @@ int run_scene_flow_dev(mod_ctx* ctx, cudaStream_t s, int w, int h, int batch, co
       fill_filter_pair(p, camera_ok, fT_prev, src.min_disparity_prev, src.max_disparity_prev);
     }
     L.first_frame = first;
-    MOD_CK(ctx, launch_scene_flow(s, L, n));
+    MOD_CK(ctx, launch_scene_flow(s, L, n, first > 0));
     ctx->launches++;
   }
   return MOD_OK;

@@ -111,7 +111,8 @@ struct ClusterStat {
 
 void launch_ray_lut(cudaStream_t s, double* d_ray_x, double* d_ray_y, float* d_ray_xf, float* d_ray_yf, int w, int h,
                     const mod_camera& cam);
-cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs);
+// follows_own_launch: the previous operation on the stream is another launch of the same batched call (disjoint frames)
+cudaError_t launch_scene_flow(cudaStream_t s, const SfLaunch& L, int n_pairs, bool follows_own_launch = false);
 cudaError_t launch_ddiv_check(cudaStream_t s, const double* a, const double* b, size_t n, unsigned long long* n_bad);
 cudaError_t launch_dynamic_map(cudaStream_t s, const float* points, size_t frame_stride_points, uint8_t* mask, int w,
                                int h, int batch, float speed_thr);
