@@ -5,9 +5,10 @@
 
 A "step" is one pass of the hot path (fused scene-flow+mask kernel, then the GPU clusterer) over one batch of
 synthetic frame pairs: by default the ZED 1280x720 sequence of BASELINE.json configs[1] (64 frames = 63 pairs per
-GPU; synthetic disparity / flow / ego-motion, seed 2002 + rank).  One process per GPU; with N > 1 every rank owns its
-own sequence (weak scaling), pixel data never crosses NVLink and the only collective is an NCCL all_gather of the
-per-frame MovingObject records, inside the timed step.
+GPU; synthetic disparity / flow / ego-motion, seed 2002).  One process per GPU; with N > 1 every rank owns its own
+batch -- the same 63 pairs, cyclically shifted by a rank-dependent offset: equal work per rank, distinguishable results
+(weak scaling) -- pixel data never crosses NVLink and the only collective is an NCCL all_gather of the per-frame
+MovingObject records, once per ring of steps and inside the timed region.
 
 Printed JSON (rank 0, one line):
   value      whole-job frame-pairs/s with inputs resident in HBM (device-timed, max over ranks)
@@ -284,7 +285,8 @@ class Workload:
     sequence (disp_prev of pair i IS disp_now of pair i-1: one buffer, what a live stereo stream looks like) or as
     independent pairs (`independent=True`: separate disp_prev buffers, BASELINE config 3's batch)."""
 
-    def __init__(self, name, pairs, dev, local_rank, seed_offset=0, independent=False, frames=None, max_batch=None):
+    def __init__(self, name, pairs, dev, local_rank, seed_offset=0, independent=False, frames=None, max_batch=None,
+                 rotate=0):
         import dataclasses
         import torch
         from moving_object_detector_b200 import (ClustererConfig, Context, OBJECT_DTYPE, STATS_DTYPE,
@@ -307,6 +309,12 @@ class Workload:
         self.transforms = [TransformMsg(t[:3], t[3:]) for t in transforms]
         self.sf_cfg, self.cl_cfg = SceneFlowConstructorConfig(), ClustererConfig()
         self.independent = independent
+        # rotate: the batch holds the same pairs in cyclically shifted order (pair slot i = pair (i + rotate) % pairs of
+        # the sequence).  Weak scaling gives every rank the SAME pairs in a different order: equal work per rank (the
+        # eight seeds 2002..2009 differ by up to 17 % in step time, profiles/r02_seed_sweep.txt, which a max over ranks
+        # would report as a scaling loss), while the gathered records stay distinguishable rank by rank.
+        order = [(i + rotate) % pairs for i in range(pairs)]
+        self.order = order
         if independent:
             self.disp_prev = disp[:pairs].clone()
             self.disp_now = disp[1:pairs + 1].clone()
@@ -319,11 +327,12 @@ class Workload:
         self.pairs_c = []
         for a in range(0, pairs, self.chunk):
             b = min(pairs, a + self.chunk)
-            self.pairs_c.append((a, b, Context.make_pairs([self.disp_now[i] for i in range(a, b)],
-                                                          [self.disp_prev[i] for i in range(a, b)],
-                                                          [flows[i] for i in range(a, b)], self.transforms[a:b],
-                                                          dts[a:b], seq["f"], seq["T"], seq["min_disparity"],
-                                                          seq["max_disparity"])))
+            sel = order[a:b]
+            self.pairs_c.append((a, b, Context.make_pairs([self.disp_now[i] for i in sel],
+                                                          [self.disp_prev[i] for i in sel],
+                                                          [flows[i] for i in sel], [self.transforms[i] for i in sel],
+                                                          [dts[i] for i in sel], seq["f"], seq["T"],
+                                                          seq["min_disparity"], seq["max_disparity"])))
         self.points = torch.empty((self.chunk, self.P, 8), dtype=torch.float32, device=dev)
         self.mask = torch.empty((self.chunk, self.P), dtype=torch.uint8, device=dev)
         self.obj_bytes, self.stat_bytes = MAX_OBJS * OBJECT_DTYPE.itemsize, STATS_DTYPE.itemsize
@@ -421,7 +430,11 @@ def main_ours(args):
         return float(t.item())
 
     # ================= headline: configs[1], weak scaling, one gather per ring of steps ===========================
-    wl = Workload(args.config, args.pairs, dev, local_rank, seed_offset=rank)
+    def rotation(r, pairs):
+        """Rank r's cyclic shift of the batch (distinct for every rank as long as pairs >= world)."""
+        return (r * max(1, pairs // world)) % pairs
+
+    wl = Workload(args.config, args.pairs, dev, local_rank, rotate=rotation(rank, args.pairs))
     B, W, H, P = wl.B, wl.W, wl.H, wl.P
     gatherer = None
     ring = max(1, min(args.gather_every, args.steps))
@@ -463,8 +476,8 @@ def main_ours(args):
     gathers = (gatherer.launches - gathers0) if gatherer else 0
     my_ms = t_start.elapsed_time(t_end)
     elapsed_ms = max_over_ranks(my_ms)
-    # weak scaling runs a different sequence on every rank, so the max over ranks also contains the spread of the
-    # data (more dynamic pixels -> a longer clusterer step); the per-rank extremes are reported beside the max
+    # every rank runs the same pairs in a rank-specific order, so the per-rank times should agree; both extremes are
+    # reported (a different SEQUENCE per rank would put the spread of the data into the max: profiles/r02_seed_sweep.txt)
     fastest_rank_ms = min_over_ranks(my_ms)
     sf_mean_ms = wl.sf_ms_per_step()
     value = B * args.steps * world / (elapsed_ms / 1e3)
@@ -481,7 +494,7 @@ def main_ours(args):
     if world > 1:
         nb = (rank + 1) % world
         mine = valid_records_bytes(last_objs.cpu().numpy(), last_stats.cpu().numpy(), OBJECT_DTYPE, STATS_DTYPE)
-        wl_nb = Workload(args.config, args.pairs, dev, local_rank, seed_offset=nb)
+        wl_nb = Workload(args.config, args.pairs, dev, local_rank, rotate=rotation(nb, args.pairs))
         wl_nb.step()
         torch.cuda.synchronize()
         want = valid_records_bytes(wl_nb.objs.cpu().numpy(), wl_nb.stats.cpu().numpy(), OBJECT_DTYPE, STATS_DTYPE)
@@ -695,7 +708,7 @@ def main_ours(args):
     if not args.no_extra:
         for name, pairs in (("gazebo_640x480", 128), ("kitti_1242x375", 256), ("zed2k_2208x1242", 32),
                             ("uhd_3840x2160", 16)):
-            wx = Workload(name, pairs, dev, local_rank, seed_offset=rank)
+            wx = Workload(name, pairs, dev, local_rank, rotate=rotation(rank, pairs))
             for _ in range(3):
                 wx.step()
             barrier()
@@ -737,7 +750,9 @@ def main_ours(args):
             "config": workload_config(args, synth.CONFIGS[args.config]),
             "l2": "inputs larger than L2 (%.0f MB read + %.0f MB written per step)" % (headline_read_mb,
                                                                                         B * P * 33 / 1e6),
-            "parallelism": f"frame-pair data parallel x{world}: rank r runs the sequence of seed {synth.CONFIGS[args.config].seed}+r",
+            "parallelism": f"frame-pair data parallel x{world}: every rank runs the {B} pairs of the seed-"
+                           f"{synth.CONFIGS[args.config].seed} sequence, rank r cyclically shifted by r*{max(1, B // world)} "
+                           f"pairs (equal work per rank, distinguishable results)",
             "roofline": {"bound": "hbm", "kernel": "scene_flow_mask_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "frac_of_8TBps_nominal": achieved / 8000.0,
