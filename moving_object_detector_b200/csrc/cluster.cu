@@ -73,6 +73,8 @@ __device__ __forceinline__ void pdl_enter() {
 #endif
 }
 
+// Callers may drop the return value as they do with <<<>>>: a failed launch is also what cudaGetLastError() reports at
+// the end of launch_cluster.
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
