@@ -736,6 +736,49 @@ def main_ours(args):
             del wx
             torch.cuda.empty_cache()
 
+    # ================= BASELINE config 4: clusterer stress (rank 0 only: it is a one-GPU, clusterer-only case) ======
+    stress = None
+    if not args.no_extra and rank == 0:
+        from moving_object_detector_b200 import ClustererConfig, Context
+        sw, sh, sframes, smax = 2208, 1242, 8, 1024
+        clouds = np.stack([synth.make_stress_cloud(sw, sh, seed=4004 + i)[0] for i in range(sframes)])
+        v = clouds[..., 4:7]
+        dyn_frac = float((np.sqrt((v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2]) >= 0.3).mean())
+        d_pts = torch.from_numpy(clouds).to(dev)
+        d_obj = torch.zeros(sframes * smax * OBJECT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        d_st = torch.zeros(sframes * STATS_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        per_n = {}
+        with Context(sw, sh, max_batch=sframes, device=local_rank) as cs:
+            for nd in (1, 4, 10):
+                ccfg = ClustererConfig(cluster_size=2500, depth_diff=0.15, dynamic_speed=0.3, neighbor_distance=nd)
+                # mask = None: the dynamic map is computed from the cloud (calculateDynamicMap), as for a foreign cloud
+                run = lambda: cs.cluster_batched_dev(sw, sh, sframes, d_pts, None, ccfg, d_obj, d_st, smax,
+                                                     stream=torch.cuda.current_stream().cuda_stream)
+                for _ in range(3):
+                    run()
+                torch.cuda.synchronize()
+                h0 = time.perf_counter()
+                a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a4.record()
+                for _ in range(10):
+                    run()
+                b4.record()
+                torch.cuda.synchronize()
+                sampler.add_window(h0, time.perf_counter())
+                st4 = np.frombuffer(d_st.cpu().numpy().tobytes(), dtype=STATS_DTYPE)
+                per_n[str(nd)] = {"ms_per_frame": a4.elapsed_time(b4) / 10 / sframes,
+                                  "objects": int(st4["n_objects"].sum()),
+                                  "frames_with_error_status": int((st4["status"] != 0).sum())}
+        stress = {"workload": f"zed2k_{sw}x{sh} clusterer stress: {sframes} frames per call with dense moving-object "
+                              f"clusters (serpentine, blobs around cluster_size, specks, checkerboards, depth steps), "
+                              f"dynamic map + clusterer on a foreign cloud, device-resident",
+                  "dynamic_fraction": dyn_frac, "frames": sframes, "by_neighbor_distance": per_n,
+                  "note": "the reference's dataCB takes 260 / 362 / 707 ms per frame of this kind on one host thread "
+                          "(profiles/r02_clusterer_stress.jsonl, 8 frames per call)"}
+        del d_pts, d_obj, d_st, clouds
+        torch.cuda.empty_cache()
+    barrier()
+
     if rank == 0:
         clocks = sampler.stop()
         algo_bytes = ALGO_BYTES_PER_PIXEL * P * B
@@ -778,6 +821,7 @@ def main_ours(args):
                        "fraction_of_pixels": filter_fallbacks / float(P * B)},
             "objects_per_step": n_objects, "frames_with_error_status": bad,
             "strong_scaling_config3": strong,
+            "clusterer_stress_config4": stress,
             "extra": {"configs": extra},
             "clocks": clocks,
         }
